@@ -1,0 +1,65 @@
+"""Oracle: DAC 44.1 kHz decode (codes -> waveform), CPU torch.
+
+Restates what `zonos/autoencoder.py:119-140` reaches in the un-vendored
+third-party dependency `transformers` (requirements.txt:30 `>=4.48.1`; 5.5.0
+installed in the build container):
+  transformers/models/dac/modeling_dac.py:345-369  quantizer.from_codes
+  :85-99    Snake1d      x + (alpha + 1e-9)^-1 * sin(alpha x)^2
+  :173-207  residual unit Snake -> Conv1d(k7, dil d, pad 3d) -> Snake -> Conv1d(k1) -> + input
+  :234-262  decoder block Snake -> ConvTranspose1d(k=2s, stride s, pad ceil(s/2)) -> 3 res units (dil 1,3,9)
+  :405-439  decoder       Conv1d(1024->1536,k7,p3) -> 4 blocks (s=8,8,4,2) -> Snake -> Conv1d(96->1,k7,p3) -> tanh
+The reference itself holds no test or golden vector for this; parity is pinned
+by outputs of `transformers.DacModel.decode` generated in the build container
+(tests/golden/make_golden.py) on seeded random-init weights.
+
+Weights: flat dict keyed like DacModel.state_dict()
+(`quantizer.quantizers.{k}.codebook.weight`, `...out_proj.{weight,bias}`,
+`decoder.conv1.*`, `decoder.block.{i}.snake1.alpha`, `decoder.block.{i}.conv_t1.*`,
+`decoder.block.{i}.res_unit{j}.{snake1,snake2}.alpha`, `...{conv1,conv2}.*`,
+`decoder.snake1.alpha`, `decoder.conv2.*`).
+"""
+import math
+import torch
+import torch.nn.functional as F
+
+STRIDES = (8, 8, 4, 2)
+DILATIONS = (1, 3, 9)
+
+
+def snake(x, alpha):
+    return x + (alpha + 1e-9).reciprocal() * torch.sin(alpha * x).pow(2)
+
+
+def from_codes(w: dict, codes: torch.Tensor) -> torch.Tensor:
+    """codes int64 [B,Q,T] -> fp32 [B,1024,T]: sum_k Conv1d_k1(Embedding_k[codes_k])."""
+    z = 0.0
+    for k in range(codes.shape[1]):
+        p = f"quantizer.quantizers.{k}."
+        lat = F.embedding(codes[:, k], w[p + "codebook.weight"]).transpose(1, 2)   # [B,8,T]
+        z = z + F.conv1d(lat, w[p + "out_proj.weight"], w[p + "out_proj.bias"])
+    return z
+
+
+def decode(w: dict, codes: torch.Tensor, taps: dict | None = None) -> torch.Tensor:
+    """codes int64 [B,Q,T] -> fp32 [B,1,512*T]  (autoencoder.py:140 adds the channel dim)."""
+    w = {k: v.float() for k, v in w.items() if k.startswith(("quantizer.", "decoder."))}
+    x = from_codes(w, codes)
+    x = F.conv1d(x, w["decoder.conv1.weight"], w["decoder.conv1.bias"], padding=3)
+    if taps is not None:
+        taps["conv1"] = x.clone()
+    for i, s in enumerate(STRIDES):
+        p = f"decoder.block.{i}."
+        x = snake(x, w[p + "snake1.alpha"])
+        x = F.conv_transpose1d(x, w[p + "conv_t1.weight"], w[p + "conv_t1.bias"], stride=s,
+                               padding=math.ceil(s / 2))
+        for j, dil in enumerate(DILATIONS, start=1):
+            r = p + f"res_unit{j}."
+            y = F.conv1d(snake(x, w[r + "snake1.alpha"]), w[r + "conv1.weight"], w[r + "conv1.bias"],
+                         dilation=dil, padding=3 * dil)
+            y = F.conv1d(snake(y, w[r + "snake2.alpha"]), w[r + "conv2.weight"], w[r + "conv2.bias"])
+            x = x + y
+        if taps is not None:
+            taps[f"block{i}"] = x.clone()
+    x = snake(x, w["decoder.snake1.alpha"])
+    x = F.conv1d(x, w["decoder.conv2.weight"], w["decoder.conv2.bias"], padding=3)
+    return torch.tanh(x)

@@ -1,0 +1,94 @@
+"""CPU: the C-ABI library loads and exports what include/zonos_b200.h declares; host-side logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT
+from oracle import codebook as o_cb
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "zonos_b200.h")).read()
+    return sorted(set(re.findall(r"ZB_API\s+[\w\s\*]+?\b(zb_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from zonos_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert set(syms) == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
+    assert _lib.load().zb_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_sizes_match_header_layout():
+    from zonos_b200 import _lib
+    assert ctypes.sizeof(_lib.zb_layer) == 8 + 14 * 8
+    assert ctypes.sizeof(_lib.zb_sampling) == 36
+    assert ctypes.sizeof(_lib.zb_cache) == 16 + 5 * 8
+    assert ctypes.sizeof(_lib.zb_gen_progress) == 16
+    assert ctypes.sizeof(_lib.zb_model_desc) == 12 * 4 + 4 + 4 + 6 * 8 + 6 * 4
+
+
+def test_no_cpu_fallback():
+    from zonos_b200 import _lib, sample_from_logits
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        _lib.context("cpu")
+    with pytest.raises(RuntimeError):
+        sample_from_logits(torch.zeros(1, 9, 1025))
+    with pytest.raises(RuntimeError):
+        _lib.Context(0)          # no device: zb_ctx_create fails loudly
+
+
+def test_host_codebook_pattern_matches_oracle():
+    from zonos_b200 import apply_delay_pattern, revert_delay_pattern
+    g = torch.Generator().manual_seed(3)
+    codes = torch.randint(-1, 1026, (2, 9, 23), generator=g)
+    d = apply_delay_pattern(codes, 1025)
+    assert (d.numpy() == o_cb.apply_delay_pattern(codes.numpy(), 1025)).all()
+    assert (revert_delay_pattern(d) == codes).all()
+
+
+def test_config_and_state_dict_names():
+    from zonos_b200 import B200ZonosBackbone, Zonos, ZonosConfig, transformer_config_dict
+    from zonos_b200.model import find_multiple
+    from zonos_b200.synthetic import TINY_DIMS, make_backbone_weights
+    assert find_multiple(1026, 8) == 1032 and find_multiple(16, 8) == 16 and find_multiple(5, 0) == 5
+    cfg = ZonosConfig.from_dict(transformer_config_dict(**TINY_DIMS))
+    assert cfg.eos_token_id == 1024 and cfg.masked_token_id == 1025 and cfg.codebook_dimension == 9
+    m = Zonos(cfg)
+    keys = set(m.state_dict())
+    assert keys == set(make_backbone_weights(**TINY_DIMS))          # the reference's checkpoint key names
+    assert "backbone.layers.0.mixer.in_proj.weight" in keys and "fused_heads.weight" in keys
+    # checkpoints store heads.{i}.weight: they are fused on load (zonos/model.py:208-223)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    fused = sd.pop("fused_heads.weight")
+    for i in range(9):
+        sd[f"heads.{i}.weight"] = fused[i * 1025:(i + 1) * 1025]
+    m2 = Zonos(cfg)
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.fused_heads.weight, fused)
+    assert isinstance(m.backbone, B200ZonosBackbone)
+
+
+def test_finalize_matches_oracle():
+    from oracle.generate import finalize_codes
+    from zonos_b200 import Zonos, ZonosConfig, transformer_config_dict
+    from zonos_b200.synthetic import TINY_DIMS
+    m = Zonos(ZonosConfig.from_dict(transformer_config_dict(**TINY_DIMS)))
+    g = torch.Generator().manual_seed(9)
+    for trial in range(20):
+        B, T = 1 + trial % 3, 30 + trial
+        delayed = torch.randint(0, 1026, (B, 9, T + 9), generator=g)
+        if trial % 2:
+            delayed[:, :, T - 8:] = 1024
+        offset = T + 9 - (trial % 5)
+        assert torch.equal(m._finalize(delayed.clone(), offset), finalize_codes(delayed.clone(), offset))

@@ -1,0 +1,255 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures recorded from the
+reference.  Integer work is bit-exact; floating point uses the tolerances written next to each assert."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (SAMPLER_CASES, build_b200_model, eos_boosted, load_golden, oracle_dims, q_stream_from_seed,
+                     sampler_inputs)
+from oracle import dac as o_dac, generate as o_gen, sampling as o_samp
+from oracle.transformer import TransformerOracle
+from zonos_b200.synthetic import (TINY_DIMS, TRANSFORMER_DIMS, make_backbone_weights, make_conditioning,
+                                  make_dac_weights)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# bf16 has 8 bits of mantissa: one rounding is 2^-9 relative.  Logits are O(1) sums of 2048 bf16 products whose
+# inputs went through 26 layers of bf16 roundings in a different accumulation order than the CPU's.
+LOGIT_ATOL = 0.06
+
+
+# ------------------------------------------------------------------------------ sampler ---------
+@pytest.mark.parametrize("i", range(len(SAMPLER_CASES)))
+def test_sampler_golden_cases(i):
+    from zonos_b200 import sample_from_logits
+    g = load_golden("sampler.npz")
+    logits, window, q = sampler_inputs(i)
+    tok = sample_from_logits(logits.to(DEV), generated_tokens=window.to(DEV), q=q.to(DEV), **SAMPLER_CASES[i])
+    assert tok.shape == (2, 9, 1) and tok.dtype == torch.int64
+    assert (tok.squeeze(-1).cpu().numpy() == g["tokens"][2 * i + 1]).all()
+
+
+@pytest.mark.parametrize("params", [dict(min_p=0.1), dict(linear=0.5, conf=0.4, quad=0.0), dict(top_p=0.9, top_k=64),
+                                    dict(temperature=0.0), dict(top_k=1), dict(min_p=0.3, temperature=0.5)])
+def test_sampler_many_rows_bit_exact(params):
+    """>= 10^4 rows per parameter set; tokens must equal the oracle's wherever its decision is not a float near-tie."""
+    from zonos_b200 import sample_from_logits
+    g = torch.Generator().manual_seed(77)
+    total = mism = ties = 0
+    for rep in range(5):
+        B = 256
+        logits = torch.randn(B, 9, 1025, generator=g) * (0.3, 1.0, 3.0, 6.0, 10.0)[rep]
+        logits[:, 1:, 1024] = -math.inf
+        window = torch.randint(0, 1026, (B, 9, 4), generator=g)
+        q = torch.empty(B, 9, 1025).exponential_(1, generator=g)
+        ref, margin = o_samp.sample_from_logits(logits.clone(), q=q, generated_tokens=window, return_margin=True, **params)
+        got = sample_from_logits(logits.to(DEV), generated_tokens=window.to(DEV), q=q.to(DEV), **params).squeeze(-1).cpu()
+        bad = got != ref
+        near = margin > 1 - 1e-4              # runner-up within 1e-4 relative of the winner: float rounding decides
+        mism += int((bad & ~near).sum()); ties += int((bad & near).sum()); total += bad.numel()
+    assert total >= 10000
+    assert mism == 0, f"{mism} real mismatches out of {total} rows ({ties} float near-ties)"
+    assert ties <= total * 1e-3
+
+
+def test_sampler_adversarial():
+    from zonos_b200 import sample_from_logits
+    B, Q, V = 4, 9, 1025
+    logits = torch.full((B, Q, V), -math.inf)
+    logits[0, :, 7] = 0.0                                   # single finite logit
+    logits[1] = 0.0                                         # all equal -> argmax(1/q)
+    logits[2] = torch.arange(V).float().repeat(Q, 1) * 1e-3
+    logits[3, :, :2] = 5.0                                  # exact tie of the two leaders
+    window = torch.tensor([7, 7]).repeat(B, Q, 1)           # duplicate token: factor 9
+    window[3] = 1025                                        # mask token clamps to 1024
+    q = torch.ones(B, Q, V)
+    q[1, :, 333] = 0.01
+    for params in (dict(min_p=0.1), dict(temperature=0.0), dict(top_p=0.5), dict(top_k=3)):
+        ref = o_samp.sample_from_logits(logits.clone(), q=q, generated_tokens=window, **params)
+        got = sample_from_logits(logits.to(DEV), generated_tokens=window.to(DEV), q=q.to(DEV), **params).squeeze(-1).cpu()
+        assert torch.equal(got, ref), params
+
+
+def test_sampler_philox_is_deterministic_and_plausible():
+    from zonos_b200 import sample_from_logits
+    logits = torch.zeros(64, 9, 1025, device=DEV)
+    a = sample_from_logits(logits, seed=5, draw_index=3)
+    b = sample_from_logits(logits, seed=5, draw_index=3)
+    c = sample_from_logits(logits, seed=5, draw_index=4)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    hist = torch.bincount(a.flatten(), minlength=1025).float()
+    assert hist.max() <= 8                                   # 576 uniform draws over 1025 bins
+
+
+# ------------------------------------------------------------------------------ embed / backbone -
+def test_embed_codes_bit_exact():
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    model = build_b200_model(TINY_DIMS, w, DEV)
+    oracle = TransformerOracle(w, oracle_dims(TINY_DIMS), torch.bfloat16)
+    codes = torch.randint(0, 1026, (3, 9, 17), generator=torch.Generator().manual_seed(1))
+    got = model.embed_codes(codes.to(DEV), repeat=2).cpu()
+    ref = oracle.embed(codes)
+    assert torch.equal(got[:3], ref) and torch.equal(got[3:], ref)      # sequential bf16 adds: exact
+
+
+@pytest.mark.parametrize("T0", [1, 5, 70])
+def test_backbone_plugin_forward_matches_oracle(T0):
+    """Reference plugin contract: allocate_inference_cache + forward(hidden, InferenceParams), prefill then decode."""
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    model = build_b200_model(TINY_DIMS, w, DEV)
+    oracle = TransformerOracle(w, oracle_dims(TINY_DIMS), torch.bfloat16)
+    R, D = 4, TINY_DIMS["d_model"]
+    g = torch.Generator().manual_seed(T0)
+    params = model.setup_cache(R, T0 + 8)
+    st = oracle.allocate(R, T0 + 8)
+    worst = 0.0
+    for T in (T0, 1, 1, 3):
+        x = torch.randn(R, T, D, generator=g).bfloat16()
+        got = model.backbone(x.to(DEV), params).float().cpu()
+        ref = oracle.forward(x, st).float()
+        worst = max(worst, (got - ref).abs().max().item())
+        params.seqlen_offset += T; params.lengths_per_sample += T
+        st.seqlen_offset += T; st.lengths += T
+    # output of the final LayerNorm is O(1); a few bf16 ulps (2^-8 at magnitude ~2-4)
+    assert worst < 0.06, worst
+
+
+def test_heads_and_cfg_mix():
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    model = build_b200_model(TINY_DIMS, w, DEV)
+    h = torch.randn(4, 1, TINY_DIMS["d_model"], generator=torch.Generator().manual_seed(2)).bfloat16()
+    ref = torch.nn.functional.linear(h[:, 0], w["fused_heads.weight"]).view(4, 9, 1025).float()
+    got = model.apply_heads(h.to(DEV))[:, :, 0].cpu()
+    assert (got - ref).abs().max() < 0.02                    # one bf16 rounding of an O(1) dot product
+
+
+# ------------------------------------------------------------------------------ generate --------
+GEN_CASES = {
+    "tiny_b1": dict(sp=dict(min_p=0.1), boost=0.0),
+    "tiny_b1_eos": dict(sp=dict(min_p=0.1), boost=5.0),
+    "tiny_b2_prefix_eos": dict(sp=dict(linear=0.5, conf=0.4, quad=0.0), boost=5.0),
+    "tiny_b1_greedy": dict(sp=dict(temperature=0.0), boost=0.0),
+}
+
+
+@pytest.mark.parametrize("name", list(GEN_CASES))
+def test_generate_matches_reference_golden(name):
+    """Whole loop vs the fixture recorded from the reference: same draws -> same delayed codes, offset and output."""
+    g = load_golden(f"generate_{name}.npz")
+    B, Lc, N, P, seed = (int(v) for v in g["meta"])
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    if GEN_CASES[name]["boost"]:
+        w = eos_boosted(w, GEN_CASES[name]["boost"])
+    model = build_b200_model(TINY_DIMS, w, DEV)
+    cond = make_conditioning(2 * B, Lc, TINY_DIMS["d_model"], seed=1234 + B)
+    prefix = torch.randint(0, 1024, (B, 9, P), generator=torch.Generator().manual_seed(7)) if P else None
+    q = q_stream_from_seed(seed, N + 9, B)
+    trace = {}
+    codes = model.generate(cond.to(DEV), prefix.to(DEV) if P else None, N, 2.0, B, dict(GEN_CASES[name]["sp"]),
+                           q_stream=q, trace=trace)
+    for j, step in enumerate(g["logit_steps"]):
+        err = np.abs(trace["logits"][int(step)].cpu().numpy() - g["logits"][j])
+        err = err[np.isfinite(err)]
+        assert err.max() < LOGIT_ATOL, (name, int(step), err.max())
+    assert trace["offset"] == int(g["offset"]), (trace["offset"], int(g["offset"]))
+    assert (trace["delayed"].cpu().numpy() == g["delayed"]).all()
+    assert codes.shape == g["codes"].shape and (codes.cpu().numpy() == g["codes"]).all()
+
+
+def test_generate_callback_and_abort():
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    model = build_b200_model(TINY_DIMS, w, DEV)
+    cond = make_conditioning(2, 9, TINY_DIMS["d_model"]).to(DEV)
+    seen = []
+    full = model.generate(cond, max_new_tokens=20, seed=3, callback=lambda f, s, m: seen.append((s, m)) or True)
+    assert [s for s, _ in seen] == list(range(1, len(seen) + 1)) and seen[0][1] == 28
+    again = model.generate(cond, max_new_tokens=20, seed=3)
+    assert torch.equal(full, again)                          # same Philox seed, chunked vs per-step host loop
+    cut = model.generate(cond, max_new_tokens=20, seed=3, callback=lambda f, s, m: s < 12)
+    assert cut.shape[2] <= 4 and torch.equal(cut, full[..., :cut.shape[2]])      # offset 13 -> valid_length 4
+
+
+def test_generate_batch_rows_are_independent():
+    """utterances never interact -> greedy B=2 equals two B=1 runs (what request sharding relies on)."""
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    model = build_b200_model(TINY_DIMS, w, DEV)
+    D = TINY_DIMS["d_model"]
+    cond = make_conditioning(4, 12, D, seed=5).to(DEV)       # rows: c0 c1 u0 u1
+    both = model.generate(cond, max_new_tokens=16, batch_size=2, sampling_params=dict(temperature=0.0))
+    for b in range(2):
+        one = model.generate(cond[[b, 2 + b]], max_new_tokens=16, batch_size=1, sampling_params=dict(temperature=0.0))
+        assert torch.equal(one[0], both[b])
+
+
+# ------------------------------------------------------------------------------ DAC -------------
+def test_dac_decode_matches_reference_golden():
+    from zonos_b200 import DACAutoencoder
+    g = load_golden("dac_decode.npz")
+    ae = DACAutoencoder(make_dac_weights(seed=1), device=DEV)
+    wav = ae.decode(torch.from_numpy(g["codes"]).to(DEV))
+    assert wav.shape == g["wav"].shape and wav.dtype == torch.float32
+    err = np.abs(wav.cpu().numpy() - g["wav"])
+    # bf16 conv operands and a bf16 residual stream (the reference's own CUDA autocast numerics) against the fp32 CPU
+    # reference: 31 layers of 2^-9 relative roundings on O(1) activations
+    assert err.max() < 0.08 and err.mean() < 0.01, (err.max(), err.mean())
+
+
+def test_dac_decode_properties():
+    """Size-independent checks at a realistic length: batch rows independent, a longer utterance shares its interior
+    with a shorter one (finite receptive field), output bounded by tanh."""
+    from zonos_b200 import DACAutoencoder
+    ae = DACAutoencoder(make_dac_weights(seed=1), device=DEV)
+    g = torch.Generator().manual_seed(4)
+    codes = torch.randint(0, 1024, (2, 9, 120), generator=g).to(DEV)
+    wav = ae.decode(codes)
+    assert wav.shape == (2, 1, 512 * 120) and wav.abs().max() <= 1.0
+    solo = ae.decode(codes[1:])
+    assert torch.equal(solo[0], wav[1])
+    short = ae.decode(codes[:, :, :60])
+    # the decoder's receptive field is < 16 frames per side, so the first 40 frames of audio agree exactly
+    assert torch.equal(short[..., :512 * 40], wav[..., :512 * 40])
+    assert ae.decode(codes[:, :, :0]).shape == (2, 1, 0)
+
+
+# ------------------------------------------------------------------------------ full size -------
+@pytest.fixture(scope="module")
+def full_model():
+    w = make_backbone_weights(**TRANSFORMER_DIMS, seed=0)
+    model = build_b200_model(TRANSFORMER_DIMS, w, DEV, dac_weights=make_dac_weights(seed=1))
+    return model, w
+
+
+def test_full_size_logits_match_oracle(full_model):
+    """Zonos-v0.1-transformer shape (26 layers, D=2048): prefill + 3 decode steps against the CPU oracle."""
+    model, w = full_model
+    oracle = TransformerOracle(w, oracle_dims(TRANSFORMER_DIMS), torch.bfloat16)
+    B, Lc, N = 1, 40, 4
+    cond = make_conditioning(2 * B, Lc, 2048)
+    q = q_stream_from_seed(420, N + 9, B)
+    trace, otrace = {}, {}
+    codes = model.generate(cond.to(DEV), max_new_tokens=N, batch_size=B, q_stream=q, trace=trace)
+    ref = o_gen.generate(oracle, cond, None, N, 2.0, B, dict(min_p=0.1), q_stream=q, trace=otrace)
+    worst = 0.0
+    for i in range(4):
+        a, b = trace["logits"][i].cpu(), otrace["logits"][i]
+        fin = torch.isfinite(b)
+        worst = max(worst, (a[fin] - b[fin]).abs().max().item())
+        if not torch.equal(trace["delayed"][..., :i + 2].cpu(), otrace["delayed"][..., :i + 2]):
+            break                                            # histories diverged at a float near-tie: stop comparing
+    assert worst < LOGIT_ATOL, worst
+    assert codes.shape == ref.shape
+
+
+def test_full_size_generate_properties(full_model):
+    model, _ = full_model
+    cond = make_conditioning(2, 64, 2048).to(DEV)
+    a = model.generate(cond, max_new_tokens=48, seed=11)
+    b = model.generate(cond, max_new_tokens=48, seed=11)
+    assert torch.equal(a, b)                                 # deterministic for a fixed seed
+    assert a.shape[0] == 1 and a.shape[1] == 9 and 0 < a.shape[2] <= 48
+    assert int(a.min()) >= 0 and int(a.max()) <= 1023
+    wav = model.autoencoder.decode(a)
+    assert wav.shape == (1, 1, 512 * a.shape[2]) and torch.isfinite(wav).all()

@@ -1,0 +1,103 @@
+"""DAC 44.1 kHz autoencoder front-end with the reference's surface (`zonos/autoencoder.py:49-170`):
+`decode(codes[B,9,T]) -> wav[B,1,512*T]` runs in libzonos_b200.so; `sampling_rate`, `num_codebooks`,
+`codebook_size` are the attributes callers read.  `encode` / `preprocess` (SURVEY.md 8(f) "next") stay on the
+`transformers` DacModel when one is attached."""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+DAC_STRIDES = (8, 8, 4, 2)
+
+
+def dac_tensor_order(n_codebooks=9, n_blocks=4) -> list[str]:
+    """state_dict keys in the order zb_dac_desc.tensors expects (include/zonos_b200.h)."""
+    keys = []
+    for k in range(n_codebooks):
+        p = f"quantizer.quantizers.{k}."
+        keys += [p + "codebook.weight", p + "out_proj.weight", p + "out_proj.bias"]
+    keys += ["decoder.conv1.weight", "decoder.conv1.bias"]
+    for i in range(n_blocks):
+        p = f"decoder.block.{i}."
+        keys += [p + "snake1.alpha", p + "conv_t1.weight", p + "conv_t1.bias"]
+        for j in (1, 2, 3):
+            r = p + f"res_unit{j}."
+            keys += [r + "snake1.alpha", r + "conv1.weight", r + "conv1.bias", r + "snake2.alpha", r + "conv2.weight", r + "conv2.bias"]
+    keys += ["decoder.snake1.alpha", "decoder.conv2.weight", "decoder.conv2.bias"]
+    return keys
+
+
+class DACAutoencoder:
+    def __init__(self, state_dict: dict | None = None, device="cuda", dac_module=None):
+        """state_dict: DacModel tensors (decode side).  None -> `DacModel.from_pretrained("descript/dac_44khz")`
+        exactly like zonos/autoencoder.py:74 (needs network / a local HF cache)."""
+        self.dac = dac_module
+        if state_dict is None:
+            from transformers.models.dac import DacModel
+            self.dac = DacModel.from_pretrained("descript/dac_44khz").eval().requires_grad_(False)
+            state_dict = self.dac.state_dict()
+        self.codebook_size = 1024
+        self.num_codebooks = sum(1 for k in state_dict if k.endswith("codebook.weight") and k.startswith("quantizer."))
+        self.sampling_rate = 44100
+        self.device = torch.device(device)
+        self._handle = None
+        self._create(state_dict)
+
+    def _create(self, sd: dict):
+        ctx = _lib.context(self.device)
+        keys = dac_tensor_order(self.num_codebooks, len(DAC_STRIDES))
+        tensors = [sd[k].detach().to(self.device, torch.float32).contiguous() for k in keys]
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        d = _lib.zb_dac_desc()
+        d.n_codebooks, d.codebook_size, d.codebook_dim = self.num_codebooks, sd[keys[0]].shape[0], sd[keys[0]].shape[1]
+        d.latent_dim, d.channels, d.n_blocks = sd[keys[1]].shape[0], sd["decoder.conv1.weight"].shape[0], len(DAC_STRIDES)
+        for i, s in enumerate(DAC_STRIDES):
+            d.strides[i] = s
+        d.tensors, d.n_tensors = arr, len(tensors)
+        self.codebook_size = int(d.codebook_size)
+        h = C.c_void_p()
+        with ctx.lock:
+            ctx.check(ctx.lib.zb_dac_create(ctx.handle, C.byref(d), C.byref(h), _lib.stream_ptr(self.device)))
+        torch.cuda.synchronize(self.device)      # the source tensors may be freed after this
+        self._handle = h
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.load().zb_dac_destroy(self._handle)
+        except Exception:
+            pass
+
+    # ---- reference surface ---------------------------------------------------------------------
+    def preprocess(self, wav: torch.Tensor, sr: int) -> torch.Tensor:
+        """zonos/autoencoder.py:80-100: resample to 44.1 kHz, left-pad to a multiple of 512."""
+        import torchaudio
+        wav = torchaudio.functional.resample(wav, sr, 44_100)
+        left = math.ceil(wav.shape[-1] / 512) * 512 - wav.shape[-1]
+        return torch.nn.functional.pad(wav, (left, 0), value=0)
+
+    def encode(self, wav: torch.Tensor) -> torch.Tensor:
+        if self.dac is None:
+            raise RuntimeError("encode needs a transformers DacModel (pass dac_module=...); only decode runs natively")
+        return self.dac.encode(wav).audio_codes
+
+    def decode(self, codes: torch.Tensor) -> torch.Tensor:
+        """zonos/autoencoder.py:119-140: int64 [B,Q,T] -> fp32 [B,1,512*T]."""
+        assert codes.dim() == 3 and codes.shape[1] == self.num_codebooks
+        codes = codes.to(self.device, torch.int64).contiguous()
+        B, _, T = codes.shape
+        up = math.prod(DAC_STRIDES)
+        wav = torch.empty((B, 1, up * T), dtype=torch.float32, device=self.device)
+        if T == 0:
+            return wav
+        ctx = _lib.context(self.device)
+        with ctx.lock:
+            ctx.check(ctx.lib.zb_dac_decode(ctx.handle, self._handle, _lib.ptr(codes), B, T, _lib.ptr(wav), _lib.stream_ptr(self.device)))
+        return wav
+
+    def decode_to_int16(self, codes: torch.Tensor):
+        """zonos/autoencoder.py:142-170."""
+        wav = self.decode(codes)[:, 0]
+        return torch.clamp(wav * 32767.0, -32767.0, 32767.0).to(torch.int16).squeeze(0).unsqueeze(1)

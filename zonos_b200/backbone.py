@@ -1,0 +1,170 @@
+"""Backbone plugin for the reference's registry (`zonos/backbone/__init__.py:24-36`).
+
+`B200ZonosBackbone` keeps the class contract the reference's `Zonos` consumes
+(`zonos/model.py:75,228,336`): `supported_architectures`, `__init__(BackboneConfig)`,
+`allocate_inference_cache(batch_size, max_seqlen, dtype) -> dict`, `forward(hidden[R,T,D], InferenceParams)`,
+and parameter names `layers.{i}.norm|mixer.in_proj|mixer.out_proj|norm2|mlp.fc1|mlp.fc2`, `norm_f`
+(`zonos/backbone/_torch.py:278-281,369-370,470-471,154-155`), so reference checkpoints load unchanged.
+All arithmetic runs in libzonos_b200.so; the nn.Modules below only OWN the weights.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import BackboneConfig, InferenceParams
+
+ROPE_TABLE_LEN = 16384   # zonos/backbone/_torch.py:206
+
+
+def rotary_table(seq_len: int, head_dim: int, base: float = 10000.0, device=None) -> torch.Tensor:
+    """fp32 [seq_len, head_dim/2, 2] = (cos, sin)(pos * base^(-2i/head_dim)) as zonos/backbone/_torch.py:29-34."""
+    inv = 1.0 / (base ** (torch.arange(0, head_dim, 2, device=device)[: head_dim // 2].float() / head_dim))
+    ang = torch.outer(torch.arange(seq_len, device=device), inv)
+    return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+
+
+class _Mixer(nn.Module):
+    def __init__(self, d_model, n_heads, n_heads_kv, head_dim):
+        super().__init__()
+        self.in_proj = nn.Linear(d_model, (n_heads + 2 * n_heads_kv) * head_dim, bias=False)
+        self.out_proj = nn.Linear(n_heads * head_dim, d_model, bias=False)
+
+
+class _MLP(nn.Module):
+    def __init__(self, d_model, d_ff):
+        super().__init__()
+        self.fc1 = nn.Linear(d_model, 2 * d_ff, bias=False)
+        self.fc2 = nn.Linear(d_ff, d_model, bias=False)
+
+
+class _Block(nn.Module):
+    def __init__(self, cfg: BackboneConfig):
+        super().__init__()
+        heads, heads_kv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
+        self.norm = nn.LayerNorm(cfg.d_model, eps=cfg.norm_epsilon)
+        self.mixer = _Mixer(cfg.d_model, heads, heads_kv, cfg.d_model // heads)
+        self.norm2 = nn.LayerNorm(cfg.d_model, eps=cfg.norm_epsilon)
+        self.mlp = _MLP(cfg.d_model, cfg.attn_mlp_d_intermediate)
+
+
+class PagedKVCache:
+    """Caller-owned paged KV memory in the layout include/zonos_b200.h documents."""
+
+    def __init__(self, n_attn_layers, rows, max_seqlen, n_heads_kv, head_dim, device, dtype=torch.bfloat16):
+        P = _lib.PAGE_TOKENS
+        self.rows = rows
+        self.pages_per_row = (max_seqlen + P - 1) // P
+        self.num_pages = rows * self.pages_per_row
+        self.kv_pages = torch.empty(n_attn_layers, self.num_pages, 2, n_heads_kv, P, head_dim, dtype=dtype, device=device)
+        # simplest allocation policy: row r owns pages [r*ppr, (r+1)*ppr); the kernels only ever go through the table
+        self.page_table = torch.arange(self.num_pages, dtype=torch.int32, device=device).view(rows, self.pages_per_row).contiguous()
+
+    def desc(self, lengths: torch.Tensor) -> _lib.zb_cache:
+        assert lengths.dtype == torch.int32 and lengths.is_cuda and lengths.numel() >= self.rows
+        d = _lib.zb_cache()
+        d.rows, d.num_pages, d.max_pages_per_row = self.rows, self.num_pages, self.pages_per_row
+        d.kv_pages, d.page_table, d.lengths = self.kv_pages.data_ptr(), self.page_table.data_ptr(), lengths.data_ptr()
+        d.conv_state = d.ssm_state = None
+        return d
+
+
+class B200ZonosBackbone(nn.Module):
+    supported_architectures = ["transformer"]
+
+    def __init__(self, config: BackboneConfig):
+        assert not config.ssm_cfg, "the hybrid (Mamba2) layers are not built yet in this round"
+        super().__init__()
+        self.config = config
+        self.layers = nn.ModuleList(_Block(config) for _ in range(config.n_layer))
+        self.norm_f = nn.LayerNorm(config.d_model, eps=config.norm_epsilon)
+        # reference quirks kept as switches: _torch.py applies out_proj twice and rotates interleaved pairs
+        self.out_proj_repeats = 2
+        self.rope_interleaved = True
+        self._native = None       # (key, handle, keepalive)
+        self._cache: PagedKVCache | None = None
+
+    # ---- native model handle ------------------------------------------------------------------
+    def _weights_key(self):
+        return tuple(p.data_ptr() for p in self.parameters()) + (self.out_proj_repeats, self.rope_interleaved)
+
+    def native_model(self, embeddings=None, heads=None, n_codebooks=9, head_vocab=1025):
+        """zb_model for the current weights (+ optional embedding tables / fused heads owned by the caller)."""
+        p0 = next(self.parameters())
+        if p0.device.type != "cuda" or p0.dtype != torch.bfloat16:
+            raise RuntimeError("B200ZonosBackbone needs bf16 weights on a CUDA device (model.to(device, torch.bfloat16))")
+        key = self._weights_key() + tuple(e.data_ptr() for e in (embeddings or [])) + ((heads.data_ptr(),) if heads is not None else ())
+        if self._native is not None and self._native[0] == key:
+            return self._native[1]
+        if self._native is not None:
+            _lib.load().zb_model_destroy(self._native[1])
+            self._native = None
+        cfg = self.config
+        ctx = _lib.context(p0.device)
+        H, Hkv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
+        hd = cfg.d_model // H
+        rope = rotary_table(ROPE_TABLE_LEN, hd, device=p0.device)
+        layers = (_lib.zb_layer * cfg.n_layer)()
+        for i, blk in enumerate(self.layers):
+            L = layers[i]
+            L.kind = 0
+            L.norm_w, L.norm_b = blk.norm.weight.data_ptr(), blk.norm.bias.data_ptr()
+            L.in_proj, L.out_proj = blk.mixer.in_proj.weight.data_ptr(), blk.mixer.out_proj.weight.data_ptr()
+            L.norm2_w, L.norm2_b = blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr()
+            L.fc1, L.fc2 = blk.mlp.fc1.weight.data_ptr(), blk.mlp.fc2.weight.data_ptr()
+        d = _lib.zb_model_desc()
+        d.d_model, d.n_layer, d.n_heads, d.n_heads_kv, d.head_dim = cfg.d_model, cfg.n_layer, H, Hkv, hd
+        d.d_ff = cfg.attn_mlp_d_intermediate
+        d.n_codebooks, d.head_vocab = n_codebooks, head_vocab
+        d.emb_vocab = embeddings[0].shape[0] if embeddings else 0
+        d.norm_kind = 0
+        d.rope_interleaved, d.out_proj_repeats = int(self.rope_interleaved), self.out_proj_repeats
+        d.norm_eps, d.rope_len, d.rope_table = cfg.norm_epsilon, ROPE_TABLE_LEN, rope.data_ptr()
+        d.layers = layers
+        d.norm_f_w, d.norm_f_b = self.norm_f.weight.data_ptr(), self.norm_f.bias.data_ptr()
+        emb_arr = None
+        if embeddings:
+            emb_arr = (C.c_void_p * len(embeddings))(*[e.data_ptr() for e in embeddings])
+            d.embeddings = emb_arr
+        d.heads = heads.data_ptr() if heads is not None else None
+        h = C.c_void_p()
+        with ctx.lock:
+            ctx.check(ctx.lib.zb_model_create(ctx.handle, C.byref(d), C.byref(h)))
+        self._native = (key, h, (rope, layers, emb_arr))
+        return h
+
+    # ---- reference plugin contract ---------------------------------------------------------------
+    def allocate_inference_cache(self, batch_size: int, max_seqlen: int, dtype: torch.dtype = torch.bfloat16):
+        """zonos/backbone/_torch.py:157-211: returns {layer: (cache, aux)}; here cache = that layer's KV pages and
+        aux = the page table.  Allocation follows the current default device like the reference (`with torch.device`)."""
+        assert dtype == torch.bfloat16, "the B200 path computes in bf16"
+        cfg = self.config
+        H, Hkv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
+        device = next(self.parameters()).device
+        self._cache = PagedKVCache(cfg.n_layer, batch_size, max_seqlen, Hkv, cfg.d_model // H, device, dtype)
+        return {i: (self._cache.kv_pages[i], self._cache.page_table) for i in range(cfg.n_layer)}
+
+    def forward(self, hidden_states: torch.Tensor, inference_params: InferenceParams, last_only: bool = False) -> torch.Tensor:
+        """zonos/backbone/_torch.py:213-238.  Positions come from `inference_params.lengths_per_sample`."""
+        assert self._cache is not None, "call allocate_inference_cache first (Zonos.setup_cache does)"
+        R, T, D = hidden_states.shape
+        assert R == self._cache.rows, f"cache was allocated for {self._cache.rows} rows, got {R}"
+        x = hidden_states.contiguous()
+        assert x.dtype == torch.bfloat16 and x.is_cuda
+        lengths = inference_params.lengths_per_sample
+        if not lengths.is_cuda:
+            raise RuntimeError("lengths_per_sample must live on the model's device")
+        model = self.native_model()
+        ctx = _lib.context(x.device)
+        y = torch.empty((R, 1 if last_only else T, D), dtype=x.dtype, device=x.device)
+        cache = self._cache.desc(lengths)
+        with ctx.lock:
+            ctx.check(ctx.lib.zb_backbone_forward(ctx.handle, model, C.byref(cache), _lib.ptr(x), T, int(last_only),
+                                                  _lib.ptr(y), _lib.stream_ptr(x.device)))
+        return y
+
+
+# Same registry shape as zonos/backbone/__init__.py:24-36.  This framework has one implementation, so every
+# name the reference knows resolves to it.
+BACKBONES = {"b200": B200ZonosBackbone, "torch": B200ZonosBackbone}

@@ -1,0 +1,614 @@
+// Backbone kernels for few activation rows (decode, and prefill as row tiles): HBM-bound weight and KV
+// streaming with 16-byte coalesced loads, fused prologues (LayerNorm/RMSNorm) and epilogues
+// (RoPE + paged KV append, residual add, SiLU gate, heads + CFG mix), warp-shuffle reductions.
+//
+// Reference call sites replaced (zonos/backbone/_torch.py): :326-328 block wiring, :401 in_proj split,
+// :57-68 RoPE, :105-106 KV write, :415 SDPA (GQA, causal), :419-420 out_proj twice, :473-474 gated MLP,
+// :238 final norm; zonos/utilities/codec_utils.py:37 embedding sum, :68-79 heads; zonos/model.py:229-233 CFG.
+// Rounding points are the reference's: every Linear / norm / SiLU / residual add rounds to bf16.
+#include "internal.h"
+
+namespace {
+
+constexpr int kWarps = 8;               // warps per GEMV CTA
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxMT = 8;               // activation rows per CTA tile
+
+__device__ __forceinline__ bool loop_idle(const zb_loop_state* st, int T_delayed) {
+  // device-driven generate: nothing to do once finished, or when this launch is the closing one (model.py:471-472)
+  return st && (st->done || st->offset + 1 >= T_delayed);
+}
+
+// ------------------------------------------------------------------ embedding sum ------------
+struct EmbedArgs {
+  const bf16* tab[16];
+  const int64_t* codes; int64_t sb, sq, st;
+  int B, T, Q, D, vocab, repeat;
+  bf16* out; int64_t out_rs;          // elements between consecutive output rows-of-T
+  const zb_loop_state* loop; int T_delayed;
+};
+
+__global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a) {
+  if (loop_idle(a.loop, a.T_delayed)) return;
+  const int b = blockIdx.x / a.T, t = blockIdx.x % a.T;
+  const int64_t col = a.loop ? (int64_t)a.loop->offset : (int64_t)t;
+  for (int d0 = threadIdx.x * 8; d0 < a.D; d0 += blockDim.x * 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = 0; k < a.Q; ++k) {
+      long long id = a.codes[b * a.sb + k * a.sq + col * a.st];
+      id = id < 0 ? 0 : (id >= a.vocab ? a.vocab - 1 : id);
+      uint4 v = *reinterpret_cast<const uint4*>(a.tab[k] + (size_t)id * a.D + d0);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {      // sequential bf16 adds: ((0 + E0) + E1) + ...  (codec_utils.py:37)
+        acc[2 * i] = rbf(acc[2 * i] + bf16lo(w[i]));
+        acc[2 * i + 1] = rbf(acc[2 * i + 1] + bf16hi(w[i]));
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+    for (int rep = 0; rep < a.repeat; ++rep)
+      *reinterpret_cast<uint4*>(a.out + (size_t)(rep * a.B + b) * a.out_rs + (size_t)t * a.D + d0) = o;
+  }
+}
+
+// ------------------------------------------------------------------ skinny GEMM (GEMV family) -
+enum { PRO_NONE = 0, PRO_NORM = 1 };
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_QKV = 2, EPI_SILU = 3, EPI_HEADS = 4 };
+
+struct GemvArgs {
+  const bf16* W;            // [N, K]
+  const bf16* x; int64_t ldx;   // activation rows; row m at x + m*ldx (HEADS: see row map)
+  int M, N, K;
+  // prologue
+  const bf16* nw; const bf16* nb; float eps; int norm_kind;
+  // EPI_STORE / EPI_RESID
+  bf16* y; int64_t ldy; const bf16* resid; int64_t ldr;
+  // EPI_QKV
+  int T;                    // tokens per cache row (m = r*T + t)
+  int Hq, Hkv, hd, rope_interleaved;
+  const float* rope; int rope_len;
+  const int32_t* lengths; const int32_t* page_table; int max_pages; int num_pages;
+  bf16* kv_layer;           // this layer's pages [num_pages][2][Hkv][64][hd]
+  bf16* q_out;              // [M, Hq*hd]
+  // EPI_SILU
+  int F;
+  // EPI_HEADS
+  int B; float cfg_scale; float* logits; int QV;
+  const zb_loop_state* loop; int T_delayed;
+};
+
+template <int MT, int PRO, int EPI>
+__global__ void __launch_bounds__(kThreads) gemv_kernel(GemvArgs a) {
+  if (loop_idle(a.loop, a.T_delayed)) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);          // [MT][K]
+  __shared__ float red[kWarps][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = a.K;
+  const int m0 = blockIdx.y * MT;
+
+  // row map: tile row i -> activation row m (HEADS with CFG pairs cond row b with uncond row B+b)
+  auto row_of = [&](int i) -> int {
+    if (EPI == EPI_HEADS && a.cfg_scale != 1.0f) {
+      const int half = MT / 2;
+      const int b = blockIdx.y * half + (i % half);
+      return (b < a.B) ? b + (i / half) * a.B : -1;
+    }
+    const int m = m0 + i;
+    return m < a.M ? m : -1;
+  };
+
+  // ---- stage activations (optionally normalised) into shared memory ----
+#pragma unroll 1
+  for (int i = 0; i < MT; ++i) {
+    const int m = row_of(i);
+    bf16* dst = xs + (size_t)i * K;
+    if (m < 0) {
+      for (int k = threadIdx.x * 8; k < K; k += kThreads * 8) *reinterpret_cast<uint4*>(dst + k) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const bf16* src = a.x + (size_t)m * a.ldx;
+    if (PRO == PRO_NONE) {
+      for (int k = threadIdx.x * 8; k < K; k += kThreads * 8)
+        *reinterpret_cast<uint4*>(dst + k) = *reinterpret_cast<const uint4*>(src + k);
+    } else {
+      // two-pass fp32 statistics over the bf16 row (nn.LayerNorm / RMSNorm semantics), output rounded to bf16
+      float s = 0.f;
+      for (int k = threadIdx.x * 8; k < K; k += kThreads * 8) {
+        uint4 v = *reinterpret_cast<const uint4*>(src + k);
+        s += bf16lo(v.x) + bf16hi(v.x) + bf16lo(v.y) + bf16hi(v.y) + bf16lo(v.z) + bf16hi(v.z) + bf16lo(v.w) + bf16hi(v.w);
+      }
+      s = warp_sum(s);
+      if (lane == 0) red[warp][0] = s;
+      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += red[w][0];
+      const float mean = (a.norm_kind == ZB_NORM_LAYERNORM) ? tot / (float)K : 0.f;
+      float sq = 0.f;
+      for (int k = threadIdx.x * 8; k < K; k += kThreads * 8) {
+        uint4 v = *reinterpret_cast<const uint4*>(src + k);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d0 = bf16lo(w4[j]) - mean, d1 = bf16hi(w4[j]) - mean;
+          sq += d0 * d0 + d1 * d1;
+        }
+      }
+      sq = warp_sum(sq);
+      if (lane == 0) red[warp][1] = sq;
+      __syncthreads();
+      float tsq = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tsq += red[w][1];
+      const float rstd = rsqrtf(tsq / (float)K + a.eps);
+      for (int k = threadIdx.x * 8; k < K; k += kThreads * 8) {
+        uint4 v = *reinterpret_cast<const uint4*>(src + k);
+        uint4 g = *reinterpret_cast<const uint4*>(a.nw + k);
+        uint4 bb = a.nb ? *reinterpret_cast<const uint4*>(a.nb + k) : make_uint4(0, 0, 0, 0);
+        const uint32_t xv[4] = {v.x, v.y, v.z, v.w}, gv[4] = {g.x, g.y, g.z, g.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float lo = (bf16lo(xv[j]) - mean) * rstd * bf16lo(gv[j]) + bf16lo(bv[j]);
+          float hi = (bf16hi(xv[j]) - mean) * rstd * bf16hi(gv[j]) + bf16hi(bv[j]);
+          o[j] = pack_bf16(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(dst + k) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+
+  // ---- weight streaming: each warp owns pairs of weight rows (n0, n1) ----
+  const int npairs = (EPI == EPI_SILU) ? a.F : (a.N + 1) / 2;
+  const int gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
+  for (int p = gw; p < npairs; p += nw) {
+    int n0, n1;
+    if (EPI == EPI_SILU) { n0 = p; n1 = p + a.F; }
+    else if (EPI == EPI_QKV && !a.rope_interleaved && p < (a.Hq + a.Hkv) * (a.hd / 2)) {
+      const int half = a.hd / 2;             // rotate-half pairs (i, i + hd/2) inside a head
+      n0 = (p / half) * a.hd + (p % half); n1 = n0 + half;
+    } else { n0 = 2 * p; n1 = 2 * p + 1; }
+    const bool has1 = n1 < a.N;
+    const bf16* w0 = a.W + (size_t)n0 * K;
+    const bf16* w1 = a.W + (size_t)(has1 ? n1 : n0) * K;
+    float acc0[MT], acc1[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
+    constexpr int U = 4;                     // 16-byte chunks in flight per weight row per lane
+    for (int kb = 0; kb < K; kb += 256 * U) {
+      uint4 a0[U], a1[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = kb + u * 256 + lane * 8;
+        if (k < K) { a0[u] = ldg_stream(w0 + k); a1[u] = ldg_stream(w1 + k); }
+        else { a0[u] = make_uint4(0, 0, 0, 0); a1[u] = make_uint4(0, 0, 0, 0); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = kb + u * 256 + lane * 8;
+        if (k < K) {
+          const uint32_t c0[4] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w};
+          const uint32_t c1[4] = {a1[u].x, a1[u].y, a1[u].z, a1[u].w};
+#pragma unroll
+          for (int i = 0; i < MT; ++i) {
+            uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)i * K + k);
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float xl = bf16lo(xw[j]), xh = bf16hi(xw[j]);
+              acc0[i] = fmaf(bf16lo(c0[j]), xl, acc0[i]);
+              acc0[i] = fmaf(bf16hi(c0[j]), xh, acc0[i]);
+              acc1[i] = fmaf(bf16lo(c1[j]), xl, acc1[i]);
+              acc1[i] = fmaf(bf16hi(c1[j]), xh, acc1[i]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) { acc0[i] = warp_sum(acc0[i]); acc1[i] = warp_sum(acc1[i]); }
+
+    // ---- epilogue: lane i finishes tile row i ----
+    if (lane < MT) {
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < MT; ++i) if (i == lane) { v0 = acc0[i]; v1 = acc1[i]; }
+      const int m = row_of(lane);
+      if (EPI == EPI_STORE) {
+        if (m >= 0) {
+          a.y[(size_t)m * a.ldy + n0] = f2bf(v0);
+          if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(v1);
+        }
+      } else if (EPI == EPI_RESID) {
+        if (m >= 0) {
+          a.y[(size_t)m * a.ldy + n0] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n0]) + rbf(v0));
+          if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n1]) + rbf(v1));
+        }
+      } else if (EPI == EPI_SILU) {
+        if (m >= 0) {
+          const float yv = rbf(v0), g = rbf(v1);
+          const float sg = rbf(g / (1.0f + expf(-g)));            // F.silu on bf16: fp32 math, bf16 result
+          a.y[(size_t)m * a.ldy + n0] = f2bf(__fmul_rn(yv, sg));
+        }
+      } else if (EPI == EPI_QKV) {
+        if (m >= 0) {
+          const int r = m / a.T, t = m % a.T;
+          const int pos = a.lengths[r] + t;
+          const int qn = a.Hq * a.hd, kn = a.Hkv * a.hd;
+          float o0 = rbf(v0), o1 = rbf(v1);
+          if (n0 < qn + kn) {                                      // q or k: rotate (_torch.py:57-68)
+            const int i = a.rope_interleaved ? (n0 % a.hd) / 2 : (n0 % a.hd);
+            const float2 cs = *reinterpret_cast<const float2*>(a.rope + ((size_t)min(pos, a.rope_len - 1) * (a.hd / 2) + i) * 2);
+            // separate fp32 mul / sub / add like the reference's eager ops (no FMA contraction)
+            const float r0 = __fsub_rn(__fmul_rn(o0, cs.x), __fmul_rn(o1, cs.y));
+            const float r1 = __fadd_rn(__fmul_rn(o1, cs.x), __fmul_rn(o0, cs.y));
+            o0 = r0; o1 = r1;
+          }
+          if (n0 < qn) {
+            a.q_out[(size_t)m * qn + n0] = f2bf(o0);
+            a.q_out[(size_t)m * qn + n1] = f2bf(o1);
+          } else {
+            const int kvsel = n0 < qn + kn ? 0 : 1;
+            const int c0i = n0 - qn - kvsel * kn, c1i = n1 - qn - kvsel * kn;
+            const int page = a.page_table[(size_t)r * a.max_pages + pos / ZB_PAGE_TOKENS];
+            bf16* base = a.kv_layer + ((size_t)page * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
+            const int tk = pos % ZB_PAGE_TOKENS;
+            base[((size_t)(c0i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c0i % a.hd)] = f2bf(o0);
+            base[((size_t)(c1i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c1i % a.hd)] = f2bf(o1);
+          }
+        }
+      } else if (EPI == EPI_HEADS) {
+        if (a.cfg_scale != 1.0f) {
+          // lanes [0,half) hold cond rows, lanes [half, MT) the matching uncond rows (model.py:230-232)
+          constexpr int half = MT / 2;
+          const float u0 = __shfl_down_sync((1u << MT) - 1, rbf(v0), half, 32);
+          const float u1 = __shfl_down_sync((1u << MT) - 1, rbf(v1), half, 32);
+          if (lane < half && m >= 0) {
+            const float c0 = rbf(v0), c1 = rbf(v1);
+            a.logits[(size_t)m * a.QV + n0] = __fadd_rn(u0, __fmul_rn(__fsub_rn(c0, u0), a.cfg_scale));
+            if (has1) a.logits[(size_t)m * a.QV + n1] = __fadd_rn(u1, __fmul_rn(__fsub_rn(c1, u1), a.cfg_scale));
+          }
+        } else if (m >= 0) {
+          a.logits[(size_t)m * a.QV + n0] = rbf(v0);
+          if (has1) a.logits[(size_t)m * a.QV + n1] = rbf(v1);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ paged attention ----------
+// grid (M, Hkv, nsplit); block = G warps (one per q head of the GQA group).  Each CTA handles the keys
+// [split*CH, (split+1)*CH) of one (row, kv head); partials are merged by the last CTA to finish.
+constexpr int kCH = ZB_PAGE_TOKENS;      // keys per split == page size, so a K (or V) tile is one contiguous 16 KB run
+constexpr int kHD = 128;
+constexpr int kKStride = kHD + 8;        // padded row stride (bf16) -> conflict-free 16 B column reads
+
+struct AttnArgs {
+  const bf16* q;            // [M, Hq*hd]
+  const bf16* kv_layer;     // pages
+  const int32_t* lengths; const int32_t* page_table; int max_pages;
+  int T, Hq, Hkv, nsplit;
+  float scale;
+  float* part;              // [M, Hq, nsplit, hd + 2]
+  int32_t* counters;        // [M, Hkv]
+  bf16* y;                  // [M, Hq*hd]
+  const zb_loop_state* loop; int T_delayed;
+};
+
+__global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
+  if (loop_idle(a.loop, a.T_delayed)) return;
+  __shared__ __align__(16) bf16 ks[kCH * kKStride];
+  __shared__ __align__(16) bf16 vs[kCH * kHD];
+  __shared__ __align__(16) float qs[8][kHD];
+  __shared__ float ps[8][kCH];
+  __shared__ int s_last;
+  const int m = blockIdx.x, g = blockIdx.y, split = blockIdx.z;
+  const int G = a.Hq / a.Hkv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = m / a.T, t = m % a.T;
+  const int kv_len = a.lengths[r] + t + 1;                 // causal: keys 0..pos inclusive
+  const int nact = (kv_len + kCH - 1) / kCH;               // splits that have keys
+  if (split >= nact) return;
+  const int k0 = split * kCH;
+  const int nk = min(kCH, kv_len - k0);
+  const int page = a.page_table[(size_t)r * a.max_pages + split];
+  const bf16* kp = a.kv_layer + (((size_t)page * 2 + 0) * a.Hkv + g) * kCH * kHD;
+  const bf16* vp = a.kv_layer + (((size_t)page * 2 + 1) * a.Hkv + g) * kCH * kHD;
+  for (int c = threadIdx.x; c < kCH * kHD / 8; c += blockDim.x) {
+    const int tok = c / (kHD / 8), d8 = (c % (kHD / 8)) * 8;
+    uint4 kvv = make_uint4(0, 0, 0, 0), vvv = make_uint4(0, 0, 0, 0);
+    if (tok < nk) { kvv = ldg_stream(kp + tok * kHD + d8); vvv = ldg_stream(vp + tok * kHD + d8); }
+    *reinterpret_cast<uint4*>(ks + tok * kKStride + d8) = kvv;
+    *reinterpret_cast<uint4*>(vs + tok * kHD + d8) = vvv;
+  }
+  const int head = g * G + warp;
+  {
+    const bf16* qp = a.q + (size_t)m * a.Hq * kHD + (size_t)head * kHD;
+    uint2 qv = *reinterpret_cast<const uint2*>(qp + lane * 4);
+    qs[warp][lane * 4 + 0] = bf16lo(qv.x); qs[warp][lane * 4 + 1] = bf16hi(qv.x);
+    qs[warp][lane * 4 + 2] = bf16lo(qv.y); qs[warp][lane * 4 + 3] = bf16hi(qv.y);
+  }
+  __syncthreads();
+  // scores: lane <-> key (2 keys per lane)
+  float sc[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int tok = lane + 32 * j;
+    float s = 0.f;
+#pragma unroll
+    for (int d8 = 0; d8 < kHD; d8 += 8) {
+      uint4 kv4 = *reinterpret_cast<const uint4*>(ks + tok * kKStride + d8);
+      const float4 q0 = *reinterpret_cast<const float4*>(&qs[warp][d8]);
+      const float4 q1 = *reinterpret_cast<const float4*>(&qs[warp][d8 + 4]);
+      s = fmaf(bf16lo(kv4.x), q0.x, s); s = fmaf(bf16hi(kv4.x), q0.y, s);
+      s = fmaf(bf16lo(kv4.y), q0.z, s); s = fmaf(bf16hi(kv4.y), q0.w, s);
+      s = fmaf(bf16lo(kv4.z), q1.x, s); s = fmaf(bf16hi(kv4.z), q1.y, s);
+      s = fmaf(bf16lo(kv4.w), q1.z, s); s = fmaf(bf16hi(kv4.w), q1.w, s);
+    }
+    sc[j] = (tok < nk) ? s * a.scale : -INFINITY;
+  }
+  const float mx = warp_max(fmaxf(sc[0], sc[1]));
+  const float p0 = __expf(sc[0] - mx), p1 = __expf(sc[1] - mx);
+  const float l = warp_sum(p0 + p1);
+  ps[warp][lane] = p0; ps[warp][lane + 32] = p1;
+  __syncwarp();
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tok = 0; tok < nk; ++tok) {
+    const float p = ps[warp][tok];
+    uint2 vv = *reinterpret_cast<const uint2*>(vs + tok * kHD + lane * 4);
+    o[0] = fmaf(p, bf16lo(vv.x), o[0]); o[1] = fmaf(p, bf16hi(vv.x), o[1]);
+    o[2] = fmaf(p, bf16lo(vv.y), o[2]); o[3] = fmaf(p, bf16hi(vv.y), o[3]);
+  }
+  float* part = a.part + (((size_t)m * a.Hq + head) * a.nsplit + split) * (kHD + 2);
+  *reinterpret_cast<float4*>(part + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  if (lane == 0) { part[kHD] = mx; part[kHD + 1] = l; }
+  // ---- last CTA of this (row, kv head) merges the splits ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t* cnt = a.counters + (size_t)m * a.Hkv + g;
+    const int prev = atomicAdd(cnt, 1);
+    s_last = (prev == nact - 1);
+    if (s_last) *cnt = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* base = a.part + (((size_t)m * a.Hq + head) * a.nsplit) * (kHD + 2);
+  float M = -INFINITY;
+  for (int s = 0; s < nact; ++s) M = fmaxf(M, __ldcg(base + (size_t)s * (kHD + 2) + kHD));
+  float L = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < nact; ++s) {
+    const float* ps_ = base + (size_t)s * (kHD + 2);
+    const float w = __expf(__ldcg(ps_ + kHD) - M);
+    L = fmaf(__ldcg(ps_ + kHD + 1), w, L);
+    const float4 ov = __ldcg(reinterpret_cast<const float4*>(ps_ + lane * 4));
+    acc[0] = fmaf(ov.x, w, acc[0]); acc[1] = fmaf(ov.y, w, acc[1]);
+    acc[2] = fmaf(ov.z, w, acc[2]); acc[3] = fmaf(ov.w, w, acc[3]);
+  }
+  const float inv = 1.0f / L;
+  uint2 outv;
+  outv.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+  outv.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+  *reinterpret_cast<uint2*>(a.y + (size_t)m * a.Hq * kHD + (size_t)head * kHD + lane * 4) = outv;
+}
+
+// ------------------------------------------------------------------ plain norm ---------------
+struct NormArgs { const bf16* x; int64_t ldx; bf16* y; int64_t ldy; const bf16* w; const bf16* b; int D; float eps; int kind; };
+__global__ void __launch_bounds__(256) norm_kernel(NormArgs a) {
+  __shared__ float red[8][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* src = a.x + (size_t)blockIdx.x * a.ldx;
+  bf16* dst = a.y + (size_t)blockIdx.x * a.ldy;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < a.D; k += 256) s += bf2f(src[k]);
+  s = warp_sum(s);
+  if (lane == 0) red[warp][0] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < 8; ++w) tot += red[w][0];
+  const float mean = a.kind == ZB_NORM_LAYERNORM ? tot / (float)a.D : 0.f;
+  float sq = 0.f;
+  for (int k = threadIdx.x; k < a.D; k += 256) { float d = bf2f(src[k]) - mean; sq += d * d; }
+  sq = warp_sum(sq);
+  if (lane == 0) red[warp][1] = sq;
+  __syncthreads();
+  float tsq = 0.f;
+  for (int w = 0; w < 8; ++w) tsq += red[w][1];
+  const float rstd = rsqrtf(tsq / (float)a.D + a.eps);
+  for (int k = threadIdx.x; k < a.D; k += 256)
+    dst[k] = f2bf((bf2f(src[k]) - mean) * rstd * bf2f(a.w[k]) + (a.b ? bf2f(a.b[k]) : 0.f));
+}
+
+// ------------------------------------------------------------------ host side ----------------
+struct Scratch {
+  bf16 *q, *attn_y, *y1, *h; float* part; int32_t* counters; int nsplit;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Scratch carve(const zb_model* mdl, void* base, int M, int nsplit, size_t* total) {
+  const zb_model_desc& d = mdl->d;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t qn = (size_t)d.n_heads * d.head_dim;
+  size_t o_q = take((size_t)M * qn * 2), o_ay = take((size_t)M * qn * 2), o_y1 = take((size_t)M * d.d_model * 2);
+  size_t o_h = take((size_t)M * d.d_ff * 2);
+  size_t o_part = take((size_t)M * d.n_heads * nsplit * (kHD + 2) * 4);
+  if (total) *total = off;
+  Scratch s{};
+  if (base) {
+    char* b = (char*)base;
+    s.q = (bf16*)(b + o_q); s.attn_y = (bf16*)(b + o_ay); s.y1 = (bf16*)(b + o_y1); s.h = (bf16*)(b + o_h);
+    s.part = (float*)(b + o_part);
+  }
+  s.nsplit = nsplit;
+  return s;
+}
+
+template <int MT, int PRO, int EPI>
+zb_status launch_gemv_t(zb_ctx* ctx, GemvArgs& a, int mtiles, cudaStream_t stream) {
+  const size_t smem = (size_t)MT * a.K * 2;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    ZB_CUDA(ctx, cudaFuncSetAttribute(gemv_kernel<MT, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int npairs = (EPI == EPI_SILU) ? a.F : (a.N + 1) / 2;
+  int gx = (npairs + kWarps - 1) / kWarps;
+  const int cap = ctx->num_sms * 2;                 // two CTAs of 8 warps per SM keep >32 KB of loads in flight
+  if (gx > cap) gx = cap;
+  dim3 grid(gx, mtiles);
+  gemv_kernel<MT, PRO, EPI><<<grid, kThreads, smem, stream>>>(a);
+  ZB_CHECK_LAUNCH(ctx);
+  return ZB_OK;
+}
+
+template <int PRO, int EPI>
+zb_status launch_gemv(zb_ctx* ctx, GemvArgs& a, cudaStream_t stream) {
+  // tile rows: HEADS pairs cond/uncond rows inside one tile, so tiles hold MT/2 utterances
+  const bool pairs = (EPI == EPI_HEADS && a.cfg_scale != 1.0f);
+  const int rows = pairs ? 2 * a.B : a.M;
+  ZB_REQUIRE(ctx, a.K % 8 == 0, "gemv: K=%d must be a multiple of 8", a.K);
+  if (rows <= 2) return launch_gemv_t<2, PRO, EPI>(ctx, a, 1, stream);
+  if (rows <= 4) return launch_gemv_t<4, PRO, EPI>(ctx, a, 1, stream);
+  const int mt = kMaxMT;
+  const int tiles = pairs ? (a.B + mt / 2 - 1) / (mt / 2) : (a.M + mt - 1) / mt;
+  return launch_gemv_t<kMaxMT, PRO, EPI>(ctx, a, tiles, stream);
+}
+
+}  // namespace
+
+size_t zb_backbone_scratch_bytes(const zb_model* model, int R, int T, int max_kv_len) {
+  size_t total = 0;
+  const int nsplit = (max_kv_len + kCH - 1) / kCH;
+  carve(model, nullptr, R * T, nsplit, &total);
+  return total;
+}
+
+zb_status zb_launch_embed(zb_ctx* ctx, const zb_embed_launch& L, cudaStream_t stream) {
+  const zb_model_desc& d = L.model->d;
+  ZB_REQUIRE(ctx, d.n_codebooks <= 16 && d.d_model % 8 == 0, "embed: unsupported dims");
+  EmbedArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int k = 0; k < d.n_codebooks; ++k) a.tab[k] = (const bf16*)L.model->emb[k];
+  a.codes = L.codes; a.sb = L.sb; a.sq = L.sq; a.st = L.st; a.B = L.B; a.T = L.T; a.Q = d.n_codebooks; a.D = d.d_model;
+  a.vocab = d.emb_vocab; a.repeat = L.repeat; a.out = L.out; a.out_rs = L.out_rs; a.loop = L.loop; a.T_delayed = L.T_delayed;
+  embed_kernel<<<L.B * L.T, 256, 0, stream>>>(a);
+  ZB_CHECK_LAUNCH(ctx);
+  return ZB_OK;
+}
+
+zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, bf16* x, int R, int T,
+                        int max_kv_len, const zb_loop_state* loop, int T_delayed, cudaStream_t stream) {
+  const zb_model_desc& d = model->d;
+  const int M = R * T;
+  ZB_REQUIRE(ctx, d.head_dim == kHD, "head_dim %d unsupported (128 only)", d.head_dim);
+  ZB_REQUIRE(ctx, d.n_heads % d.n_heads_kv == 0 && d.n_heads / d.n_heads_kv <= 8, "GQA group size unsupported");
+  ZB_REQUIRE(ctx, cache && cache->rows >= R, "cache has %d rows, need %d", cache ? cache->rows : 0, R);
+  const int nsplit = (max_kv_len + kCH - 1) / kCH;
+  ZB_REQUIRE(ctx, nsplit <= cache->max_pages_per_row, "sequence of %d tokens exceeds the page table (%d pages)", max_kv_len,
+             cache->max_pages_per_row);
+  size_t need = 0;
+  carve(model, nullptr, M, nsplit, &need);
+  ZB_REQUIRE(ctx, ctx->scratch_bytes >= need, "internal: scratch not reserved (%zu < %zu)", ctx->scratch_bytes, need);
+  Scratch s = carve(model, ctx->scratch, M, nsplit, nullptr);
+  ZB_REQUIRE(ctx, (size_t)M * d.n_heads_kv <= ZB_NUM_COUNTERS, "too many rows (%d) for the attention merge counters", M);
+  s.counters = ctx->counters;     // always zero between launches (the merging CTA resets its word)
+  const size_t page_elems = (size_t)2 * d.n_heads_kv * ZB_PAGE_TOKENS * d.head_dim;
+  const int qn = d.n_heads * d.head_dim;
+  const int G = d.n_heads / d.n_heads_kv;
+
+  for (int li = 0; li < d.n_layer; ++li) {
+    const zb_layer& L = model->layers[li];
+    ZB_REQUIRE(ctx, L.kind == ZB_LAYER_ATTENTION, "layer %d: only attention layers are implemented in this build", li);
+    bf16* kv_layer = (bf16*)cache->kv_pages + (size_t)model->attn_index[li] * cache->num_pages * page_elems;
+    GemvArgs a;
+    // 1. norm -> in_proj -> RoPE -> KV append (+ q)
+    memset(&a, 0, sizeof(a));
+    a.W = (const bf16*)L.in_proj; a.x = x; a.ldx = d.d_model; a.M = M; a.N = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim; a.K = d.d_model;
+    a.nw = (const bf16*)L.norm_w; a.nb = (const bf16*)L.norm_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
+    a.T = T; a.Hq = d.n_heads; a.Hkv = d.n_heads_kv; a.hd = d.head_dim; a.rope_interleaved = d.rope_interleaved;
+    a.rope = d.rope_table; a.rope_len = d.rope_len; a.lengths = cache->lengths; a.page_table = cache->page_table;
+    a.max_pages = cache->max_pages_per_row; a.num_pages = cache->num_pages; a.kv_layer = kv_layer; a.q_out = s.q;
+    a.loop = loop; a.T_delayed = T_delayed;
+    if (zb_status st = launch_gemv<PRO_NORM, EPI_QKV>(ctx, a, stream)) return st;
+    // 2. attention over the paged cache
+    {
+      AttnArgs at;
+      memset(&at, 0, sizeof(at));
+      at.q = s.q; at.kv_layer = kv_layer; at.lengths = cache->lengths; at.page_table = cache->page_table;
+      at.max_pages = cache->max_pages_per_row; at.T = T; at.Hq = d.n_heads; at.Hkv = d.n_heads_kv; at.nsplit = nsplit;
+      at.scale = 1.0f / sqrtf((float)d.head_dim); at.part = s.part; at.counters = s.counters; at.y = s.attn_y;
+      at.loop = loop; at.T_delayed = T_delayed;
+      dim3 grid(M, d.n_heads_kv, nsplit);
+      attn_kernel<<<grid, 32 * G, 0, stream>>>(at);
+      ZB_CHECK_LAUNCH(ctx);
+    }
+    // 3. out_proj (x repeats), the last one adds the residual
+    const bf16* src = s.attn_y;
+    for (int rep = 0; rep < d.out_proj_repeats; ++rep) {
+      memset(&a, 0, sizeof(a));
+      a.W = (const bf16*)L.out_proj; a.x = src; a.ldx = qn; a.M = M; a.N = d.d_model; a.K = qn;
+      a.loop = loop; a.T_delayed = T_delayed;
+      if (rep == d.out_proj_repeats - 1) {
+        a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model;
+        if (zb_status st = launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, stream)) return st;
+      } else {
+        ZB_REQUIRE(ctx, qn == d.d_model, "out_proj_repeats > 1 needs H*hd == D");
+        bf16* dst = (src == s.y1) ? s.attn_y : s.y1;
+        a.y = dst; a.ldy = d.d_model;
+        if (zb_status st = launch_gemv<PRO_NONE, EPI_STORE>(ctx, a, stream)) return st;
+        src = dst;
+      }
+    }
+    // 4. norm2 -> fc1 -> value * silu(gate)
+    memset(&a, 0, sizeof(a));
+    a.W = (const bf16*)L.fc1; a.x = x; a.ldx = d.d_model; a.M = M; a.N = 2 * d.d_ff; a.K = d.d_model; a.F = d.d_ff;
+    a.nw = (const bf16*)L.norm2_w; a.nb = (const bf16*)L.norm2_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
+    a.y = s.h; a.ldy = d.d_ff; a.loop = loop; a.T_delayed = T_delayed;
+    if (zb_status st = launch_gemv<PRO_NORM, EPI_SILU>(ctx, a, stream)) return st;
+    // 5. fc2 + residual
+    memset(&a, 0, sizeof(a));
+    a.W = (const bf16*)L.fc2; a.x = s.h; a.ldx = d.d_ff; a.M = M; a.N = d.d_model; a.K = d.d_ff;
+    a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model; a.loop = loop; a.T_delayed = T_delayed;
+    if (zb_status st = launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, stream)) return st;
+  }
+  return ZB_OK;
+}
+
+zb_status zb_launch_final_norm(zb_ctx* ctx, const zb_model* model, const bf16* x, int R, int T, int last_only, bf16* y,
+                               cudaStream_t stream) {
+  const zb_model_desc& d = model->d;
+  NormArgs a;
+  a.w = (const bf16*)d.norm_f_w; a.b = (const bf16*)d.norm_f_b; a.D = d.d_model; a.eps = d.norm_eps; a.kind = d.norm_kind;
+  if (last_only) { a.x = x + (size_t)(T - 1) * d.d_model; a.ldx = (int64_t)T * d.d_model; a.y = y; a.ldy = d.d_model; }
+  else { a.x = x; a.ldx = d.d_model; a.y = y; a.ldy = d.d_model; }
+  norm_kernel<<<last_only ? R : R * T, 256, 0, stream>>>(a);
+  ZB_CHECK_LAUNCH(ctx);
+  return ZB_OK;
+}
+
+zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden, int64_t row_stride, int R, int apply_norm,
+                          float cfg_scale, float* logits, const zb_loop_state* loop, int T_delayed, cudaStream_t stream) {
+  const zb_model_desc& d = model->d;
+  GemvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.W = (const bf16*)d.heads; a.x = hidden; a.ldx = row_stride; a.M = R; a.N = d.n_codebooks * d.head_vocab; a.K = d.d_model;
+  a.nw = (const bf16*)d.norm_f_w; a.nb = (const bf16*)d.norm_f_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
+  a.cfg_scale = cfg_scale; a.logits = logits; a.QV = a.N; a.loop = loop; a.T_delayed = T_delayed;
+  if (cfg_scale != 1.0f) {
+    ZB_REQUIRE(ctx, R % 2 == 0, "CFG needs an even number of rows");
+    a.B = R / 2;
+  } else a.B = R;
+  if (apply_norm) return launch_gemv<PRO_NORM, EPI_HEADS>(ctx, a, stream);
+  return launch_gemv<PRO_NONE, EPI_HEADS>(ctx, a, stream);
+}

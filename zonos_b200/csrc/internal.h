@@ -1,0 +1,64 @@
+// Internal launcher interfaces between the translation units of libzonos_b200.so.
+#pragma once
+#include "common.cuh"
+
+// Device-resident loop state of one generate() session (see sampler.cu, zonos/model.py:439-509).
+#define ZB_MAX_B 256
+struct zb_loop_state {
+  int32_t offset;      // model.py `offset`: column of `delayed` written last
+  int32_t step_idx;    // loop iteration about to run
+  int32_t done;        // loop finished
+  int32_t steps;       // model.py `step`
+  int32_t draw_idx;    // sample calls made so far (index into q_stream / logits_trace)
+  int32_t arrive;      // last-CTA counter
+  int32_t max_steps;
+  int32_t _pad;
+  long long remaining[ZB_MAX_B];
+  int32_t stopping[ZB_MAX_B];
+};
+
+struct zb_model {
+  zb_ctx* ctx;
+  zb_model_desc d;
+  std::vector<zb_layer> layers;
+  std::vector<const void*> emb;
+  int n_attn = 0, n_mamba = 0;
+  std::vector<int> attn_index;    // layer -> index among attention layers (or -1)
+  std::vector<int> mamba_index;
+};
+
+struct zb_sample_launch {
+  const float* logits = nullptr; int B = 0, Q = 0, V = 0;
+  const int64_t* window = nullptr; int64_t wsb = 0, wsq = 0; int W = 0;
+  const float* q = nullptr; uint64_t seed = 0, draw_index = 0;
+  zb_sampling sp{}; int apply_bias = 0; int64_t* tokens = nullptr;
+  zb_loop_state* st = nullptr; int64_t* delayed = nullptr; int T = 0; int ctx_len = 0;
+  int32_t* lengths = nullptr; const float* q_stream = nullptr; int q_calls = 0;
+  float* logits_trace = nullptr; int trace_calls = 0; int first = 0; int prefix_len = 0;
+  int32_t* mirror = nullptr;   // host-mapped copy of the first 8 words of zb_loop_state (device pointer)
+};
+zb_status zb_launch_sample(zb_ctx* ctx, const zb_sample_launch& L, cudaStream_t stream);
+
+// ---- backbone pieces (decode.cu) ----
+struct zb_embed_launch {
+  const zb_model* model; const int64_t* codes; int64_t sb, sq, st; int B, T, repeat; bf16* out;
+  int64_t out_rs;             // elements between consecutive output rows (>= T*D)
+  const zb_loop_state* loop = nullptr; int T_delayed = 0;   // loop mode: column = loop->offset
+};
+zb_status zb_launch_embed(zb_ctx* ctx, const zb_embed_launch& L, cudaStream_t stream);
+
+// Runs all layers on the residual stream x[M=R*T, D] in place (scratch-resident), appending K/V.
+// loop != null: every kernel exits early once the loop is done (device-driven generate).
+// max_kv_len: host upper bound of lengths[r] + T (sizes the split-KV grid).
+zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, bf16* x, int R, int T, int max_kv_len,
+                        const zb_loop_state* loop, int T_delayed, cudaStream_t stream);
+// y[R or R*T rows] = final norm(x)
+zb_status zb_launch_final_norm(zb_ctx* ctx, const zb_model* model, const bf16* x, int R, int T, int last_only, bf16* y,
+                               cudaStream_t stream);
+// logits = heads(norm_f?(hidden)) with the CFG mix.  hidden row r at hidden + r*row_stride.
+zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden, int64_t row_stride, int R,
+                          int apply_norm, float cfg_scale, float* logits, const zb_loop_state* loop, int T_delayed,
+                          cudaStream_t stream);
+size_t zb_backbone_scratch_bytes(const zb_model* model, int R, int T, int max_kv_len);
+
+// ---- DAC (dac.cu) ----

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the Zonos inference hot path on B200 (contract: the driver's prompt, section "Measurement").
+
+A "step" is ONE pass of the hot path over one batch of synthetic utterances: prefill of the conditioning prefix,
+the whole autoregressive loop (N = 861 frames = 10 s of audio) and the DAC decode of the result.
+Workload at N=1 GPU = BASELINE.json configs[1]: Zonos-v0.1-transformer, bf16, batch 1 with CFG 2.0, Lc = 160
+synthetic conditioning tokens.  With --gpus N every rank runs the same per-GPU workload on its own utterances
+(request sharding, no collective on the data path) => "scaling": "weak".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--frames F] [--cond-len Lc]
+  python bench.py --impl reference ...      # the CPU oracle port of the reference path, timed on host cores
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAME_RATE = 44100 / 512          # 86.13 codec frames per audio second
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=861, help="new frames per utterance (861 = 10 s)")
+    ap.add_argument("--cond-len", type=int, default=160)
+    ap.add_argument("--ref-frames", type=int, default=32, help="frames per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=26, help="(debug) fewer layers; invalidates the number")
+    return ap.parse_args()
+
+
+def config_dict(args, n_gpus):
+    return {"workload": "Zonos-v0.1-transformer random-init bf16, CFG 2.0, %d utterance(s)/GPU x %d frames (%.1f s) + DAC 44.1 kHz decode"
+                        % (args.batch, args.frames, args.frames / FRAME_RATE),
+            "baseline_config": "configs[1]" if args.batch == 1 else "configs[3]-shaped",
+            "batch_per_gpu": args.batch, "frames": args.frames, "cond_len": args.cond_len, "cfg_scale": 2.0,
+            "sampling": "min_p=0.1, repetition_penalty=3.0 (generate defaults)", "n_layer": args.layers,
+            "parallelism": "request-sharded replicas x%d, no data-path collective" % n_gpus,
+            "l2": "each decode step streams 3.2 GB of weights (>> 126 MB L2), no flush needed"}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference): the reference's algorithm restated in oracle/
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_setup(args):
+    import torch
+    from oracle.transformer import BackboneDims, TransformerOracle
+    from zonos_b200.synthetic import TRANSFORMER_DIMS, make_backbone_weights, make_conditioning, make_dac_weights
+    dims = dict(TRANSFORMER_DIMS, n_layer=args.layers)
+    torch.set_num_threads(os.cpu_count())
+    w = make_backbone_weights(**dims, seed=0, heads_scale=8.0, eos_off=True)
+    oracle = TransformerOracle(w, BackboneDims(**dims), torch.bfloat16)
+    cond = make_conditioning(2, args.cond_len, dims["d_model"])
+    return oracle, cond, make_dac_weights(seed=1), w
+
+
+def cpu_oracle_step(oracle, cond, dacw, frames):
+    """One bounded sample of the workload on the CPU: batch 1, `frames` new frames + their DAC decode."""
+    import torch
+    from oracle import dac as o_dac, generate as o_gen
+    torch.manual_seed(420)
+    t0 = time.perf_counter()
+    codes = o_gen.generate(oracle, cond, None, frames, 2.0, 1, dict(min_p=0.1))
+    o_dac.decode(dacw, codes)
+    dt = time.perf_counter() - t0
+    return codes.shape[2] / FRAME_RATE, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is Python and
+    cannot travel to the GPU box) with all host threads, same config/metric, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    oracle, cond, dacw, _ = cpu_oracle_setup(args)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_oracle_step(oracle, cond, dacw, max(4, args.ref_frames // 4))
+    audio = t = 0.0
+    for _ in range(args.steps):
+        a, d = cpu_oracle_step(oracle, cond, dacw, args.ref_frames)
+        audio += a; t += d
+    value = audio / t
+    sample = "batch 1, Lc=%d prefill + %d frames + DAC decode per step (of the %d-frame utterance)" % (
+        args.cond_len, args.ref_frames, args.frames)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from zonos_b200 import DACAutoencoder, Zonos, ZonosConfig, _lib, transformer_config_dict
+    from zonos_b200.synthetic import TRANSFORMER_DIMS, make_backbone_weights, make_conditioning, make_dac_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    dims = dict(TRANSFORMER_DIMS, n_layer=args.layers)
+    B, N, Lc = args.batch, args.frames, args.cond_len
+
+    # every rank builds the same replica (seeded CPU generator) - no weight broadcast needed for synthetic runs
+    w = make_backbone_weights(**dims, seed=0, heads_scale=8.0, eos_off=True)
+    dacw = make_dac_weights(seed=1)
+    model = Zonos(ZonosConfig.from_dict(transformer_config_dict(**dims)), autoencoder=DACAutoencoder(dacw, device=dev))
+    model = model.to(dev, torch.bfloat16)
+    model.load_state_dict(w)
+    cond_host = make_conditioning(2 * B, Lc, dims["d_model"], seed=1234 + rank).pin_memory()
+    cond_dev = cond_host.to(dev)
+    ctx = model._ctx()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device(seed):
+        codes = model.generate(cond_dev, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
+        wav = model.autoencoder.decode(codes)
+        return codes, wav
+
+    wav_host = torch.empty((B, 1, 512 * N), dtype=torch.float32).pin_memory()
+
+    def step_e2e(seed):
+        c = cond_host.to(dev, non_blocking=True)                       # H2D inside the timed region
+        codes = model.generate(c, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
+        wav = model.autoencoder.decode(codes)
+        wav_host[..., : wav.shape[-1]].copy_(wav, non_blocking=True)   # D2H of the result
+        torch.cuda.current_stream(dev).synchronize()
+        return codes, wav
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, K):
+        barrier()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        frames = 0
+        for i in range(K):
+            codes, _ = fn(1000 + i)
+            frames += codes.shape[0] * codes.shape[2]
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count() - l0
+        barrier()
+        t = torch.tensor([ms, float(frames)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            return float(tmax[0]), float(tsum[1]), launches
+        return ms, float(frames), launches
+
+    for i in range(max(args.warmup, 3)):
+        step_device(i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, frames, launches = timed(step_device, args.steps)
+    clock_info = clocks.stop() if rank == 0 else None
+    value = (frames / FRAME_RATE) / (ms / 1e3)
+
+    step_e2e(7)
+    ms_e, frames_e, _ = timed(step_e2e, args.steps)
+    e2e = (frames_e / FRAME_RATE) / (ms_e / 1e3)
+
+    # ---- roofline leg: the dominant decode kernel (norm2 + fc1 + SiLU GEMV, 55 % of the weight bytes) timed ALONE
+    # with CUDA events, cycling over the layers so every launch streams its 67 MB from HBM (26 x 67 MB >> L2) ----
+    roof = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        native = model._native_model()
+        sp = _lib.stream_ptr(dev)
+        R = 2 * B if 2 * B <= 8 else 8
+        iters = 8 * dims["n_layer"]
+        for it in range(dims["n_layer"]):
+            ctx.check(ctx.lib.zb_bench_kernel(ctx.handle, native, it % dims["n_layer"], 2, R, sp))
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for it in range(iters):
+            ctx.check(ctx.lib.zb_bench_kernel(ctx.handle, native, it % dims["n_layer"], 2, R, sp))
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        us = 1e3 * e0.elapsed_time(e1) / iters
+        fc1_bytes = 2 * dims["d_ff"] * dims["d_model"] * 2 + R * dims["d_model"] * 2 + R * dims["d_ff"] * 2 + 4 * dims["d_model"]
+        achieved = fc1_bytes / (us * 1e-6) / 1e9
+        # whole decode step, for context: algorithmic bytes per step over the measured step time
+        per_layer = (dims["n_heads"] + 2 * dims["n_heads_kv"]) * 128 * dims["d_model"] + dims["d_model"] ** 2 \
+            + 3 * dims["d_ff"] * dims["d_model"]
+        w_bytes = 2 * (dims["n_layer"] * per_layer + 9 * 1025 * dims["d_model"])
+        mean_s = Lc + 1 + (N + 8) / 2
+        kv_bytes = 2 * B * mean_s * dims["n_layer"] * 2 * dims["n_heads_kv"] * 128 * 2
+        step_bytes = w_bytes + kv_bytes
+        steps_per_utt = N + 8
+        roof = {"bound": "hbm", "kernel": "gemv_kernel<MT=%d, PRO_NORM, EPI_SILU> (norm2+fc1+SiLU)" % (2 if R <= 2 else 4 if R <= 4 else 8),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "us_per_launch": us, "algorithmic_bytes_per_launch": fc1_bytes,
+                "decode_step": {"algorithmic_bytes": step_bytes, "ms_incl_prefill_and_dac": ms / args.steps / steps_per_utt,
+                                "achieved_gbs_lower_bound": step_bytes / (ms / args.steps / steps_per_utt * 1e-3) / 1e9}}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        del w
+        oracle, cond, dacw_c, _ = cpu_oracle_setup(args)
+        a, d = cpu_oracle_step(oracle, cond, dacw_c, args.ref_frames)
+        cpu = {"value": a / d, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "batch 1, Lc=%d prefill + %d frames + DAC decode (%.1f s of CPU work)" % (Lc, args.ref_frames, d)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": config_dict(args, n_gpus), "frames_per_second": frames / (ms / 1e3),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cond_host.numel() * 2, "d2h_bytes_per_step": wav_host.numel() * 4,
+                        "ms_per_step": ms_e / args.steps},
+                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

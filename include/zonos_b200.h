@@ -233,6 +233,12 @@ ZB_API zb_status zb_dac_destroy(zb_dac* dac);
 ZB_API zb_status zb_dac_decode(zb_ctx* ctx, const zb_dac* dac, const int64_t* codes, int32_t B, int32_t T, float* wav,
                         zb_stream stream);
 
+/* ------------------------------------------------------------------ diagnostics -------------- */
+/* Launches ONE production decode kernel of `layer` on scratch activations with `rows` activation rows (1..8), so a
+ * benchmark can time it alone with CUDA events: which = 1 out_proj GEMV, 2 norm2+fc1+SiLU GEMV, 3 fc2+residual GEMV. */
+ZB_API zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows,
+                                 zb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

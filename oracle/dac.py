@@ -40,9 +40,21 @@ def from_codes(w: dict, codes: torch.Tensor) -> torch.Tensor:
     return z
 
 
-def decode(w: dict, codes: torch.Tensor, taps: dict | None = None) -> torch.Tensor:
-    """codes int64 [B,Q,T] -> fp32 [B,1,512*T]  (autoencoder.py:140 adds the channel dim)."""
+def _r(x):
+    """Round to bf16 and back: one rounding point of the reference's CUDA autocast path."""
+    return x.bfloat16().float()
+
+
+def decode(w: dict, codes: torch.Tensor, taps: dict | None = None, autocast_bf16: bool = False) -> torch.Tensor:
+    """codes int64 [B,Q,T] -> fp32 [B,1,512*T]  (autoencoder.py:140 adds the channel dim).
+
+    autocast_bf16=False is the reference's CPU path (autocast disabled, autoencoder.py:138 -> full fp32).
+    autocast_bf16=True emulates the dtype flow of its CUDA path (`torch.autocast(cuda, bf16)`):
+    conv operands and results rounded to bf16, fp32 accumulation, Snake evaluated in fp32 on the bf16 activation,
+    bf16 residual adds.  (The final tanh and the codebook-projection sum are left in fp32.)"""
     w = {k: v.float() for k, v in w.items() if k.startswith(("quantizer.", "decoder."))}
+    if autocast_bf16:
+        return _decode_autocast(w, codes)
     x = from_codes(w, codes)
     x = F.conv1d(x, w["decoder.conv1.weight"], w["decoder.conv1.bias"], padding=3)
     if taps is not None:
@@ -63,3 +75,23 @@ def decode(w: dict, codes: torch.Tensor, taps: dict | None = None) -> torch.Tens
     x = snake(x, w["decoder.snake1.alpha"])
     x = F.conv1d(x, w["decoder.conv2.weight"], w["decoder.conv2.bias"], padding=3)
     return torch.tanh(x)
+
+
+def _decode_autocast(w: dict, codes: torch.Tensor) -> torch.Tensor:
+    def conv(x, name, **kw):
+        return _r(F.conv1d(_r(x), _r(w[name + ".weight"]), None, **kw) + w[name + ".bias"].view(1, -1, 1))
+
+    x = _r(from_codes(w, codes))
+    x = conv(x, "decoder.conv1", padding=3)
+    for i, s in enumerate(STRIDES):
+        p = f"decoder.block.{i}."
+        x = snake(x, w[p + "snake1.alpha"])
+        x = _r(F.conv_transpose1d(_r(x), _r(w[p + "conv_t1.weight"]), None, stride=s, padding=math.ceil(s / 2))
+               + w[p + "conv_t1.bias"].view(1, -1, 1))
+        for j, dil in enumerate(DILATIONS, start=1):
+            r = p + f"res_unit{j}."
+            y = conv(snake(x, w[r + "snake1.alpha"]), r + "conv1", dilation=dil, padding=3 * dil)
+            y = conv(snake(y, w[r + "snake2.alpha"]), r + "conv2")
+            x = _r(x + y)
+    x = snake(x, w["decoder.snake1.alpha"])
+    return torch.tanh(conv(x, "decoder.conv2", padding=3))

@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(GemvArgs a) {
 constexpr int kCH = ZB_PAGE_TOKENS;      // keys per split == page size, so a K (or V) tile is one contiguous 16 KB run
 constexpr int kHD = 128;
 constexpr int kKStride = kHD + 8;        // padded row stride (bf16) -> conflict-free 16 B column reads
+constexpr int kPart = kHD + 4;           // floats per split partial: o[128], max, sum, pad (keeps float4 alignment)
 
 struct AttnArgs {
   const bf16* q;            // [M, Hq*hd]
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
     o[0] = fmaf(p, bf16lo(vv.x), o[0]); o[1] = fmaf(p, bf16hi(vv.x), o[1]);
     o[2] = fmaf(p, bf16lo(vv.y), o[2]); o[3] = fmaf(p, bf16hi(vv.y), o[3]);
   }
-  float* part = a.part + (((size_t)m * a.Hq + head) * a.nsplit + split) * (kHD + 2);
+  float* part = a.part + (((size_t)m * a.Hq + head) * a.nsplit + split) * kPart;
   *reinterpret_cast<float4*>(part + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
   if (lane == 0) { part[kHD] = mx; part[kHD + 1] = l; }
   // ---- last CTA of this (row, kv head) merges the splits ----
@@ -382,12 +383,12 @@ __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const float* base = a.part + (((size_t)m * a.Hq + head) * a.nsplit) * (kHD + 2);
+  const float* base = a.part + (((size_t)m * a.Hq + head) * a.nsplit) * kPart;
   float M = -INFINITY;
-  for (int s = 0; s < nact; ++s) M = fmaxf(M, __ldcg(base + (size_t)s * (kHD + 2) + kHD));
+  for (int s = 0; s < nact; ++s) M = fmaxf(M, __ldcg(base + (size_t)s * kPart + kHD));
   float L = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int s = 0; s < nact; ++s) {
-    const float* ps_ = base + (size_t)s * (kHD + 2);
+    const float* ps_ = base + (size_t)s * kPart;
     const float w = __expf(__ldcg(ps_ + kHD) - M);
     L = fmaf(__ldcg(ps_ + kHD + 1), w, L);
     const float4 ov = __ldcg(reinterpret_cast<const float4*>(ps_ + lane * 4));
@@ -442,7 +443,7 @@ Scratch carve(const zb_model* mdl, void* base, int M, int nsplit, size_t* total)
   const size_t qn = (size_t)d.n_heads * d.head_dim;
   size_t o_q = take((size_t)M * qn * 2), o_ay = take((size_t)M * qn * 2), o_y1 = take((size_t)M * d.d_model * 2);
   size_t o_h = take((size_t)M * d.d_ff * 2);
-  size_t o_part = take((size_t)M * d.n_heads * nsplit * (kHD + 2) * 4);
+  size_t o_part = take((size_t)M * d.n_heads * nsplit * kPart * 4);
   if (total) *total = off;
   Scratch s{};
   if (base) {
@@ -611,4 +612,34 @@ zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden
   } else a.B = R;
   if (apply_norm) return launch_gemv<PRO_NORM, EPI_HEADS>(ctx, a, stream);
   return launch_gemv<PRO_NONE, EPI_HEADS>(ctx, a, stream);
+}
+
+// ---- diagnostics: launch ONE production kernel on scratch activations (bench.py roofline leg) ----
+extern "C" zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows, zb_stream stream) {
+  if (!ctx) return ZB_ERR_INVALID;
+  ZB_REQUIRE(ctx, model && layer >= 0 && layer < model->d.n_layer && rows >= 1 && rows <= 8, "zb_bench_kernel: bad arguments");
+  const zb_model_desc& d = model->d;
+  const zb_layer& L = model->layers[layer];
+  const size_t need = zb_backbone_scratch_bytes(model, rows, 1, ZB_PAGE_TOKENS) + (size_t)rows * d.d_model * 2 + 256;
+  if (zb_status st = zb_scratch_reserve(ctx, need)) return st;
+  Scratch s = carve(model, ctx->scratch, rows, 1, nullptr);
+  bf16* x = (bf16*)((char*)ctx->scratch + (ctx->scratch_bytes - (((size_t)rows * d.d_model * 2 + 255) / 256 * 256)));
+  GemvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = rows;
+  if (which == 2) {          // norm2 -> fc1 -> value * silu(gate)
+    a.W = (const bf16*)L.fc1; a.x = x; a.ldx = d.d_model; a.N = 2 * d.d_ff; a.K = d.d_model; a.F = d.d_ff;
+    a.nw = (const bf16*)L.norm2_w; a.nb = (const bf16*)L.norm2_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
+    a.y = s.h; a.ldy = d.d_ff;
+    return launch_gemv<PRO_NORM, EPI_SILU>(ctx, a, (cudaStream_t)stream);
+  } else if (which == 3) {   // fc2 + residual
+    a.W = (const bf16*)L.fc2; a.x = s.h; a.ldx = d.d_ff; a.N = d.d_model; a.K = d.d_ff;
+    a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model;
+    return launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, (cudaStream_t)stream);
+  } else if (which == 1) {   // out_proj
+    a.W = (const bf16*)L.out_proj; a.x = s.attn_y; a.ldx = d.n_heads * d.head_dim; a.N = d.d_model; a.K = d.n_heads * d.head_dim;
+    a.y = s.y1; a.ldy = d.d_model;
+    return launch_gemv<PRO_NONE, EPI_STORE>(ctx, a, (cudaStream_t)stream);
+  }
+  return zb_fail(ctx, ZB_ERR_INVALID, "zb_bench_kernel: unknown kernel id %d", which);
 }

@@ -436,10 +436,11 @@ zb_status zb_launch_sample(zb_ctx* ctx, const zb_sample_launch& L, cudaStream_t 
   ZB_REQUIRE(ctx, L.B >= 1, "sampler: B=%d", L.B);
   size_t smem = 0;
   if (L.sp.temperature > 0.f && (L.sp.top_p > 0.f || L.sp.top_k > 0)) smem = (size_t)L.Q * SAMP_SORTN * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ZB_CUDA(ctx, cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SAMP_SORTN * 8));
-    attr_set = true;
+  ZB_REQUIRE(ctx, smem <= 227 * 1024, "sampler: top-p/top-k with Q=%d codebooks needs %zu bytes of shared memory", L.Q, smem);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    ZB_CUDA(ctx, cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
   }
   sample_kernel<<<L.B, 32 * L.Q, smem, stream>>>(a);
   ZB_CHECK_LAUNCH(ctx);

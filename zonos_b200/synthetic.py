@@ -23,7 +23,7 @@ def _uniform(gen, shape, bound, dtype):
 
 def make_backbone_weights(d_model=2048, n_layer=26, n_heads=16, n_heads_kv=4, d_ff=8192,
                           n_codebooks=9, head_vocab=1025, emb_vocab=1032, seed=0,
-                          dtype=torch.bfloat16, heads_scale=1.0) -> dict:
+                          dtype=torch.bfloat16, heads_scale=1.0, eos_off=False) -> dict:
     g = torch.Generator().manual_seed(seed)
     hd = d_model // n_heads
     w = {}
@@ -41,6 +41,15 @@ def make_backbone_weights(d_model=2048, n_layer=26, n_heads=16, n_heads_kv=4, d_
     for k in range(n_codebooks):
         w[f"embeddings.{k}.weight"] = torch.randn(emb_vocab, d_model, generator=g).to(dtype)
     w["fused_heads.weight"] = _uniform(g, (n_codebooks * head_vocab, d_model), heads_scale / math.sqrt(d_model), dtype)
+    if eos_off:
+        # Throughput runs want a deterministic length: pin one coordinate of the final norm's output
+        # to a constant (weight 0, bias 8) and let ONLY the codebook-0 EOS head row read it with a large negative
+        # weight, so that logit is ~ -240 on every step and EOS is never sampled.
+        w["backbone.norm_f.weight"][0] = 0.0
+        w["backbone.norm_f.bias"][0] = 8.0
+        w["fused_heads.weight"][:, 0] = 0.0
+        w["fused_heads.weight"][head_vocab - 1] = 0.0
+        w["fused_heads.weight"][head_vocab - 1, 0] = -30.0
     return w
 
 

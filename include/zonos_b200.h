@@ -234,10 +234,11 @@ ZB_API zb_status zb_dac_decode(zb_ctx* ctx, const zb_dac* dac, const int64_t* co
                         zb_stream stream);
 
 /* ------------------------------------------------------------------ diagnostics -------------- */
-/* Launches ONE production decode kernel of `layer` on scratch activations with `rows` activation rows (1..8), so a
- * benchmark can time it alone with CUDA events: which = 1 out_proj GEMV, 2 norm2+fc1+SiLU GEMV, 3 fc2+residual GEMV. */
+/* Launches ONE production decode kernel `iters` times back to back (layer, layer+1, ... cyclically, so every launch
+ * streams its weights from HBM) on scratch activations with `rows` activation rows (1..8), so a benchmark can time it
+ * alone with CUDA events: which = 1 out_proj GEMV, 2 norm2+fc1+SiLU GEMV, 3 fc2+residual GEMV. */
 ZB_API zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows,
-                                 zb_stream stream);
+                                 int32_t iters, zb_stream stream);
 
 #ifdef __cplusplus
 }

@@ -79,7 +79,7 @@ PROTOTYPES = {
     "zb_dac_create": (c_int32, [c_void_p, C.POINTER(zb_dac_desc), C.POINTER(c_void_p), c_void_p]),
     "zb_dac_destroy": (c_int32, [c_void_p]),
     "zb_dac_decode": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
-    "zb_bench_kernel": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "zb_bench_kernel": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
 }
 
 _lib = None

@@ -100,3 +100,137 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
 // Programmatic dependent launch (PDL): wait for the producer grid / let the consumer grid start early
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// L2 prefetch of `bytes` (multiple of 16) starting at p: pulls weights HBM -> L2 ahead of the dependency wait
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in the
+// stream is still running and must call pdl_wait() before touching anything the predecessor writes.
+template <typename... KArgs, typename... Args>
+inline cudaError_t zb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// ---- mbarrier + bulk-copy (TMA engine, UBLKCP) helpers ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a lost transaction must end in a trap (an error the host sees), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins > (1u << 24)) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy (bytes % 16 == 0, both sides 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+// Reduce V (power of two) per-lane values across the warp with V-1 + (5 - log2 V) shuffles instead of 5*V:
+// every halving step trades half of the values with the xor-partner.  On return v[0] of lane L holds the full sum of
+// value index multi_reduce_index<V>(L) (all lanes sharing that index hold the same number).
+template <int V>
+__device__ __forceinline__ void warp_reduce_multi(float (&v)[V]) {
+  constexpr int LOGV = (V == 1) ? 0 : (V == 2) ? 1 : (V == 4) ? 2 : (V == 8) ? 3 : 4;
+  static_assert((1 << LOGV) == V && V <= 16, "V must be a power of two <= 16");
+  const int lane = threadIdx.x & 31;
+  int n = V;
+#pragma unroll
+  for (int s = 0; s < LOGV; ++s) {
+    const int o = 16 >> s;
+    const bool upper = (lane & o) != 0;
+    n >>= 1;
+#pragma unroll
+    for (int j = 0; j < V / 2; ++j) {
+      if (j < n) {
+        const float keep = upper ? v[j + n] : v[j];
+        const float send = upper ? v[j] : v[j + n];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16 >> LOGV; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+template <int V>
+__device__ __forceinline__ int multi_reduce_index(int lane) {
+  constexpr int LOGV = (V == 1) ? 0 : (V == 2) ? 1 : (V == 4) ? 2 : (V == 8) ? 3 : 4;
+  int idx = 0;
+#pragma unroll
+  for (int s = 0; s < LOGV; ++s) idx += ((lane >> (4 - s)) & 1) * (V >> (s + 1));
+  return idx;
+}
+
+// ---- packed fp32x2 FMA (sm_100: FFMA2) ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float sum_f32x2(unsigned long long v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return a + b;
+}
+// raw 32-bit shared-address forms (no generic->shared conversion inside hot loops)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins > (1u << 24)) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }

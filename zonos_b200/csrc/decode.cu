@@ -6,6 +6,8 @@
 // :57-68 RoPE, :105-106 KV write, :415 SDPA (GQA, causal), :419-420 out_proj twice, :473-474 gated MLP,
 // :238 final norm; zonos/utilities/codec_utils.py:37 embedding sum, :68-79 heads; zonos/model.py:229-233 CFG.
 // Rounding points are the reference's: every Linear / norm / SiLU / residual add rounds to bf16.
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace {
@@ -29,6 +31,8 @@ struct EmbedArgs {
 };
 
 __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (loop_idle(a.loop, a.T_delayed)) return;
   const int b = blockIdx.x / a.T, t = blockIdx.x % a.T;
   const int64_t col = a.loop ? (int64_t)a.loop->offset : (int64_t)t;
@@ -79,10 +83,77 @@ struct GemvArgs {
   // EPI_HEADS
   int B; float cfg_scale; float* logits; int QV;
   const zb_loop_state* loop; int T_delayed;
+  int ring_stages, prefetch_ahead;      // gemv3: stages in the shared-memory ring, stages prefetched into L2 beyond it
 };
+
+
+// Finishes one output pair (n0, n1) of activation row m from the fp32 dot products v0, v1.  Rounding points are the
+// reference's (bf16 Linear output first, then the fused op).  HEADS with CFG: m is the utterance, (v0,v1) its cond
+// row and (u0,u1) its uncond row.
+template <int EPI>
+__device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, int m, int n0, int n1, bool has1, float v0, float v1,
+                                              float u0, float u1) {
+  if (EPI == EPI_STORE) {
+    a.y[(size_t)m * a.ldy + n0] = f2bf(v0);
+    if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(v1);
+  } else if (EPI == EPI_RESID) {
+    a.y[(size_t)m * a.ldy + n0] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n0]) + rbf(v0));
+    if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n1]) + rbf(v1));
+  } else if (EPI == EPI_SILU) {
+    const float yv = rbf(v0), g = rbf(v1);
+    const float sg = rbf(g / (1.0f + expf(-g)));            // F.silu on bf16: fp32 math, bf16 result
+    a.y[(size_t)m * a.ldy + n0] = f2bf(__fmul_rn(yv, sg));
+  } else if (EPI == EPI_QKV) {
+    const int r = m / a.T, t = m % a.T;
+    const int pos = a.lengths[r] + t;
+    const int qn = a.Hq * a.hd, kn = a.Hkv * a.hd;
+    float o0 = rbf(v0), o1 = rbf(v1);
+    if (n0 < qn + kn) {                                      // q or k: rotate (_torch.py:57-68)
+      const int i = a.rope_interleaved ? (n0 % a.hd) / 2 : (n0 % a.hd);
+      const float2 cs = *reinterpret_cast<const float2*>(a.rope + ((size_t)min(pos, a.rope_len - 1) * (a.hd / 2) + i) * 2);
+      // separate fp32 mul / sub / add like the reference's eager ops (no FMA contraction)
+      const float r0 = __fsub_rn(__fmul_rn(o0, cs.x), __fmul_rn(o1, cs.y));
+      const float r1 = __fadd_rn(__fmul_rn(o1, cs.x), __fmul_rn(o0, cs.y));
+      o0 = r0; o1 = r1;
+    }
+    if (n0 < qn) {
+      a.q_out[(size_t)m * qn + n0] = f2bf(o0);
+      a.q_out[(size_t)m * qn + n1] = f2bf(o1);
+    } else {
+      const int kvsel = n0 < qn + kn ? 0 : 1;
+      const int c0i = n0 - qn - kvsel * kn, c1i = n1 - qn - kvsel * kn;
+      const int page = a.page_table[(size_t)r * a.max_pages + pos / ZB_PAGE_TOKENS];
+      bf16* base = a.kv_layer + ((size_t)page * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
+      const int tk = pos % ZB_PAGE_TOKENS;
+      base[((size_t)(c0i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c0i % a.hd)] = f2bf(o0);
+      base[((size_t)(c1i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c1i % a.hd)] = f2bf(o1);
+    }
+  } else if (EPI == EPI_HEADS) {
+    if (a.cfg_scale != 1.0f) {                               // u + (c - u) * s in fp32 (model.py:230-232)
+      const float c0 = rbf(v0), c1 = rbf(v1), w0 = rbf(u0), w1 = rbf(u1);
+      a.logits[(size_t)m * a.QV + n0] = __fadd_rn(w0, __fmul_rn(__fsub_rn(c0, w0), a.cfg_scale));
+      if (has1) a.logits[(size_t)m * a.QV + n1] = __fadd_rn(w1, __fmul_rn(__fsub_rn(c1, w1), a.cfg_scale));
+    } else {
+      a.logits[(size_t)m * a.QV + n0] = rbf(v0);
+      if (has1) a.logits[(size_t)m * a.QV + n1] = rbf(v1);
+    }
+  }
+}
+
+// Weight-row pair of unit p (see gemv kernels): SiLU pairs value row with gate row, rotate-half RoPE pairs (i, i+hd/2).
+template <int EPI>
+__device__ __forceinline__ void unit_rows(const GemvArgs& a, int p, int& n0, int& n1) {
+  if (EPI == EPI_SILU) { n0 = p; n1 = p + a.F; }
+  else if (EPI == EPI_QKV && !a.rope_interleaved && p < (a.Hq + a.Hkv) * (a.hd / 2)) {
+    const int half = a.hd / 2;
+    n0 = (p / half) * a.hd + (p % half); n1 = n0 + half;
+  } else { n0 = 2 * p; n1 = 2 * p + 1; }
+}
 
 template <int MT, int PRO, int EPI>
 __global__ void __launch_bounds__(kThreads) gemv_kernel(GemvArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (loop_idle(a.loop, a.T_delayed)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* xs = reinterpret_cast<bf16*>(smem_raw);          // [MT][K]
@@ -170,11 +241,7 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(GemvArgs a) {
   const int gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
   for (int p = gw; p < npairs; p += nw) {
     int n0, n1;
-    if (EPI == EPI_SILU) { n0 = p; n1 = p + a.F; }
-    else if (EPI == EPI_QKV && !a.rope_interleaved && p < (a.Hq + a.Hkv) * (a.hd / 2)) {
-      const int half = a.hd / 2;             // rotate-half pairs (i, i + hd/2) inside a head
-      n0 = (p / half) * a.hd + (p % half); n1 = n0 + half;
-    } else { n0 = 2 * p; n1 = 2 * p + 1; }
+    unit_rows<EPI>(a, p, n0, n1);
     const bool has1 = n1 < a.N;
     const bf16* w0 = a.W + (size_t)n0 * K;
     const bf16* w1 = a.W + (size_t)(has1 ? n1 : n0) * K;
@@ -221,65 +288,239 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(GemvArgs a) {
 #pragma unroll
       for (int i = 0; i < MT; ++i) if (i == lane) { v0 = acc0[i]; v1 = acc1[i]; }
       const int m = row_of(lane);
-      if (EPI == EPI_STORE) {
-        if (m >= 0) {
-          a.y[(size_t)m * a.ldy + n0] = f2bf(v0);
-          if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(v1);
-        }
-      } else if (EPI == EPI_RESID) {
-        if (m >= 0) {
-          a.y[(size_t)m * a.ldy + n0] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n0]) + rbf(v0));
-          if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n1]) + rbf(v1));
-        }
-      } else if (EPI == EPI_SILU) {
-        if (m >= 0) {
-          const float yv = rbf(v0), g = rbf(v1);
-          const float sg = rbf(g / (1.0f + expf(-g)));            // F.silu on bf16: fp32 math, bf16 result
-          a.y[(size_t)m * a.ldy + n0] = f2bf(__fmul_rn(yv, sg));
-        }
-      } else if (EPI == EPI_QKV) {
-        if (m >= 0) {
-          const int r = m / a.T, t = m % a.T;
-          const int pos = a.lengths[r] + t;
-          const int qn = a.Hq * a.hd, kn = a.Hkv * a.hd;
-          float o0 = rbf(v0), o1 = rbf(v1);
-          if (n0 < qn + kn) {                                      // q or k: rotate (_torch.py:57-68)
-            const int i = a.rope_interleaved ? (n0 % a.hd) / 2 : (n0 % a.hd);
-            const float2 cs = *reinterpret_cast<const float2*>(a.rope + ((size_t)min(pos, a.rope_len - 1) * (a.hd / 2) + i) * 2);
-            // separate fp32 mul / sub / add like the reference's eager ops (no FMA contraction)
-            const float r0 = __fsub_rn(__fmul_rn(o0, cs.x), __fmul_rn(o1, cs.y));
-            const float r1 = __fadd_rn(__fmul_rn(o1, cs.x), __fmul_rn(o0, cs.y));
-            o0 = r0; o1 = r1;
-          }
-          if (n0 < qn) {
-            a.q_out[(size_t)m * qn + n0] = f2bf(o0);
-            a.q_out[(size_t)m * qn + n1] = f2bf(o1);
-          } else {
-            const int kvsel = n0 < qn + kn ? 0 : 1;
-            const int c0i = n0 - qn - kvsel * kn, c1i = n1 - qn - kvsel * kn;
-            const int page = a.page_table[(size_t)r * a.max_pages + pos / ZB_PAGE_TOKENS];
-            bf16* base = a.kv_layer + ((size_t)page * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
-            const int tk = pos % ZB_PAGE_TOKENS;
-            base[((size_t)(c0i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c0i % a.hd)] = f2bf(o0);
-            base[((size_t)(c1i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c1i % a.hd)] = f2bf(o1);
-          }
-        }
-      } else if (EPI == EPI_HEADS) {
-        if (a.cfg_scale != 1.0f) {
-          // lanes [0,half) hold cond rows, lanes [half, MT) the matching uncond rows (model.py:230-232)
-          constexpr int half = MT / 2;
-          const float u0 = __shfl_down_sync((1u << MT) - 1, rbf(v0), half, 32);
-          const float u1 = __shfl_down_sync((1u << MT) - 1, rbf(v1), half, 32);
-          if (lane < half && m >= 0) {
-            const float c0 = rbf(v0), c1 = rbf(v1);
-            a.logits[(size_t)m * a.QV + n0] = __fadd_rn(u0, __fmul_rn(__fsub_rn(c0, u0), a.cfg_scale));
-            if (has1) a.logits[(size_t)m * a.QV + n1] = __fadd_rn(u1, __fmul_rn(__fsub_rn(c1, u1), a.cfg_scale));
-          }
-        } else if (m >= 0) {
-          a.logits[(size_t)m * a.QV + n0] = rbf(v0);
-          if (has1) a.logits[(size_t)m * a.QV + n1] = rbf(v1);
+      if (EPI == EPI_HEADS && a.cfg_scale != 1.0f) {
+        // lanes [0,half) hold cond rows, lanes [half, MT) the matching uncond rows (model.py:230-232)
+        constexpr int half = MT / 2;
+        const float u0 = __shfl_down_sync((1u << MT) - 1, v0, half, 32);
+        const float u1 = __shfl_down_sync((1u << MT) - 1, v1, half, 32);
+        if (lane < half && m >= 0) gemv_epilogue<EPI>(a, m, n0, n1, has1, v0, v1, u0, u1);
+      } else if (m >= 0) {
+        gemv_epilogue<EPI>(a, m, n0, n1, has1, v0, v1, 0.f, 0.f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ decode GEMV (M <= 4 rows) ---
+// One CTA per SM-sized slice of the weight matrix; the slice streams through a shared-memory ring filled by the
+// TMA engine (cp.async.bulk + mbarrier, producer warp) and drained by 16 consumer warps.  Consumers keep their
+// k-slice of all R activation rows as fp32 pairs in REGISTERS; the inner loop is LDS.128 + bf16->fp32 shifts +
+// packed FFMA2 only, every stage is full (no per-row branches) and V = RW*R lane-partials are reduced with one
+// butterfly per stage.
+// PDL: weights do not depend on the previous kernel, so the producer fills the whole ring BEFORE
+// griddepcontrol.wait - the HBM stream of kernel N+1 overlaps the tail and launch latency of kernel N.
+// Weights are read once per step: their loads carry an L2 evict_first policy so KV and activations stay in L2.
+constexpr int kW3 = 16;                      // consumer warps
+constexpr int kMaxStages = 24;               // ring stages are a launch parameter (a.ring_stages); stage = RG*RW weight rows
+
+template <int EPI>
+__device__ __forceinline__ int units_total(const GemvArgs& a) {
+  return (EPI == EPI_SILU) ? a.F : (EPI == EPI_QKV) ? a.N / 2 : a.N;     // pairs only where the epilogue couples rows
+}
+// local row index -> weight row, for the CTA whose units are [u_begin, ...)
+template <int EPI>
+__device__ __forceinline__ int row_of_local(const GemvArgs& a, int u_begin, int lr) {
+  if (EPI == EPI_SILU || EPI == EPI_QKV) {
+    int n0, n1;
+    unit_rows<EPI>(a, u_begin + (lr >> 1), n0, n1);
+    return (lr & 1) ? n1 : n0;
+  }
+  return u_begin + lr;
+}
+
+template <int R, int NC, int RW, int PRO, int EPI>
+__global__ void __launch_bounds__((kW3 + 1) * 32, (R * NC <= 2) ? 2 : 1) gemv3_kernel(GemvArgs a) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) unsigned char smem3[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ float red[2][kW3][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = a.K;
+  const int row_bytes = K * 2;
+  constexpr int Kc = NC * 256;
+  const int KS = K / Kc;                                       // k-slices; RG = kW3 / KS row groups
+  const int RPS = (kW3 / KS) * RW;                             // weight rows per stage
+  const int kStageBytes = RPS * row_bytes;
+  const int kStages = a.ring_stages;
+  const int kPrefetchAhead = a.prefetch_ahead;
+  constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
+  const int nunits = units_total<EPI>(a);
+  const int u_begin = (int)((long long)blockIdx.x * nunits / gridDim.x);
+  const int u_end = (int)((long long)(blockIdx.x + 1) * nunits / gridDim.x);
+  const int nrows = (u_end - u_begin) * (kPairs ? 2 : 1);
+  const int nstage = (nrows + RPS - 1) / RPS;
+  unsigned char* ring = smem3;
+  float* part = reinterpret_cast<float*>(smem3 + (size_t)kStages * kStageBytes);   // [nstage*RPS][KS][R]
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kW3); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kW3) {
+    // ===== producer warp drives the TMA engine; every stage is filled completely (tail rows repeat the last row,
+    // their results are never read) so the consumers run branch-free.  Lane q issues the copy of row q of a stage
+    // (the issue cost of a stage's copies is paid once per warp instruction); lane 0 arms the barrier first. =====
+    const uint64_t pol = l2_evict_first_policy();
+    for (int st = 0; st < nstage; ++st) {
+      const int slot = st % kStages;
+      if (st >= kStages) mbar_wait(&empty_bar[slot], ((st / kStages) - 1) & 1);
+      const int r0 = st * RPS;
+      if (lane == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)kStageBytes);
+      __syncwarp();
+      unsigned char* dst = ring + (size_t)slot * kStageBytes;
+      if (!kPairs && r0 + RPS <= nrows) {                     // contiguous rows: one copy per stage
+        if (lane == 0) bulk_g2s(dst, a.W + (size_t)(u_begin + r0) * K, (uint32_t)kStageBytes, &full_bar[slot], pol);
+      } else {
+        for (int q = lane; q < RPS; q += 32) {
+          const int lr = min(r0 + q, nrows - 1);
+          bulk_g2s(dst + (size_t)q * row_bytes, a.W + (size_t)row_of_local<EPI>(a, u_begin, lr) * K, row_bytes, &full_bar[slot], pol);
         }
       }
+      if (kPrefetchAhead > 0 && st >= kStages - 1) {           // optional rolling L2 prefetch beyond the ring
+        const int first = (st == kStages - 1) ? kStages : st + kPrefetchAhead;
+        const int last = (st == kStages - 1) ? kStages + kPrefetchAhead : st + kPrefetchAhead + 1;
+        for (int ps = first; ps < last && ps < nstage; ++ps)
+          for (int q = lane; q < RPS && ps * RPS + q < nrows; q += 32)
+            prefetch_l2(a.W + (size_t)row_of_local<EPI>(a, u_begin, ps * RPS + q) * K, row_bytes);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int ks = warp % KS, rg = warp / KS;
+  const size_t koff = (size_t)ks * Kc;
+  pdl_wait();                                                  // activations / loop state come from the predecessor
+  const bool idle = loop_idle(a.loop, a.T_delayed);            // still drain the ring: the producer already filled it
+
+  // this warp's k-slice of the R activation rows as fp32 pairs: lane holds k = koff + c*256 + lane*8 + [0,8)
+  float xf[R][NC * 8];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const uint4 v = (i < a.M && !idle) ? *reinterpret_cast<const uint4*>(a.x + (size_t)i * a.ldx + koff + c * 256 + lane * 8)
+                                         : make_uint4(0, 0, 0, 0);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xf[i][c * 8 + 2 * j] = bf16lo(w4[j]); xf[i][c * 8 + 2 * j + 1] = bf16hi(w4[j]); }
+    }
+  if (PRO == PRO_NORM) {
+    // two-pass fp32 statistics over the bf16 row (nn.LayerNorm / RMSNorm), result rounded to bf16 like the reference
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int e = 0; e < NC * 8; ++e) sacc += xf[i][e];
+      sacc = warp_sum(sacc);
+      if (rg == 0 && lane == 0) red[0][ks][i] = sacc;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");      // consumer warps only
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float tot = 0.f;
+      for (int q = 0; q < KS; ++q) tot += red[0][q][i];
+      mean[i] = (a.norm_kind == ZB_NORM_LAYERNORM) ? tot / (float)K : 0.f;
+      float sq = 0.f;
+#pragma unroll
+      for (int e = 0; e < NC * 8; ++e) { const float d = xf[i][e] - mean[i]; sq += d * d; }
+      sq = warp_sum(sq);
+      if (rg == 0 && lane == 0) red[1][ks][i] = sq;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float tsq = 0.f;
+      for (int q = 0; q < KS; ++q) tsq += red[1][q][i];
+      rstd[i] = rsqrtf(tsq / (float)K + a.eps);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const size_t k = koff + c * 256 + lane * 8;
+      const uint4 g = *reinterpret_cast<const uint4*>(a.nw + k);
+      const uint4 bb = a.nb ? *reinterpret_cast<const uint4*>(a.nb + k) : make_uint4(0, 0, 0, 0);
+      const uint32_t gv[4] = {g.x, g.y, g.z, g.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g0 = bf16lo(gv[j]), g1 = bf16hi(gv[j]), b0 = bf16lo(bv[j]), b1 = bf16hi(bv[j]);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          xf[i][c * 8 + 2 * j] = rbf((xf[i][c * 8 + 2 * j] - mean[i]) * rstd[i] * g0 + b0);
+          xf[i][c * 8 + 2 * j + 1] = rbf((xf[i][c * 8 + 2 * j + 1] - mean[i]) * rstd[i] * g1 + b1);
+        }
+      }
+    }
+  }
+  unsigned long long x2[R][NC * 4];                            // (even k, odd k) pairs for FFMA2
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int e = 0; e < NC * 4; ++e) x2[i][e] = pack_f32x2(xf[i][2 * e], xf[i][2 * e + 1]);
+
+  constexpr int V = RW * R;                                    // values each warp reduces per stage
+  const int my_idx = multi_reduce_index<V>(lane);
+  const bool writer = (lane & ((32 / V) - 1)) == 0;
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  // lane's first weight byte inside a stage: row rg*RW, k = koff + lane*8
+  const uint32_t lane_base = smem_u32(ring) + (uint32_t)(rg * RW) * row_bytes + (uint32_t)(koff + lane * 8) * 2;
+  // where this lane stores its reduced value: part[(r0 + rg*RW + w)*KS + ks][i], w = my_idx / R, i = my_idx % R
+  const uint32_t part_lane = smem_u32(part) + (uint32_t)((((rg * RW + my_idx / R) * KS + ks) * R + my_idx % R) * 4);
+  const uint32_t part_stage = (uint32_t)(RPS * KS * R * 4);
+  uint32_t slot = 0, phase = 0;
+  for (int st = 0; st < nstage; ++st) {
+    mbar_wait_u32(full0 + slot * 8, phase);
+    const uint32_t src = lane_base + slot * kStageBytes;
+    unsigned long long acc2[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc2[q] = 0ull;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const uint4 wv = lds128(src + w * row_bytes + c * 512);
+        const uint32_t c0[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const unsigned long long w2 = pack_f32x2(bf16lo(c0[jj]), bf16hi(c0[jj]));
+#pragma unroll
+          for (int i = 0; i < R; ++i) ffma2(acc2[w * R + i], w2, x2[i][c * 4 + jj]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_u32(empty0 + slot * 8);           // weights are consumed: release the slot before reducing
+    float acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = sum_f32x2(acc2[q]);
+    warp_reduce_multi<V>(acc);
+    if (writer) sts32(part_lane + st * part_stage, acc[0]);
+    if (++slot == (uint32_t)kStages) { slot = 0; phase ^= 1; }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  if (idle) return;
+
+  // ---- combine the k-slices and finish: one thread per (unit, activation row) ----
+  const bool cfg = (EPI == EPI_HEADS && a.cfg_scale != 1.0f);
+  const int rows_out = cfg ? a.B : a.M;
+  const int nu = u_end - u_begin;
+  for (int t = threadIdx.x; t < nu * rows_out; t += kW3 * 32) {
+    const int j = t / rows_out, i = t % rows_out;
+    int n0, n1;
+    float v0 = 0.f, v1 = 0.f, u0 = 0.f, u1 = 0.f;
+    if (kPairs) {
+      unit_rows<EPI>(a, u_begin + j, n0, n1);
+      const float* s0 = part + (size_t)(2 * j) * KS * R;
+      const float* s1 = s0 + (size_t)KS * R;
+      for (int q = 0; q < KS; ++q) { v0 += s0[q * R + i]; v1 += s1[q * R + i]; }
+      gemv_epilogue<EPI>(a, i, n0, n1, true, v0, v1, 0.f, 0.f);
+    } else {
+      n0 = u_begin + j; n1 = n0 + 1;
+      const float* s0 = part + (size_t)j * KS * R;
+      for (int q = 0; q < KS; ++q) { v0 += s0[q * R + i]; if (cfg) u0 += s0[q * R + a.B + i]; }
+      gemv_epilogue<EPI>(a, i, n0, n1, false, v0, v1, u0, u1);
     }
   }
 }
@@ -305,6 +546,8 @@ struct AttnArgs {
 };
 
 __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (loop_idle(a.loop, a.T_delayed)) return;
   __shared__ __align__(16) bf16 ks[kCH * kKStride];
   __shared__ __align__(16) bf16 vs[kCH * kHD];
@@ -468,9 +711,64 @@ zb_status launch_gemv_t(zb_ctx* ctx, GemvArgs& a, int mtiles, cudaStream_t strea
   const int cap = ctx->num_sms * 2;                 // two CTAs of 8 warps per SM keep >32 KB of loads in flight
   if (gx > cap) gx = cap;
   dim3 grid(gx, mtiles);
-  gemv_kernel<MT, PRO, EPI><<<grid, kThreads, smem, stream>>>(a);
-  ZB_CHECK_LAUNCH(ctx);
+  ZB_CUDA(ctx, zb_launch_pdl(gemv_kernel<MT, PRO, EPI>, grid, dim3(kThreads), smem, stream, a));
+  ctx->launches++;
   return ZB_OK;
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int R, int NC, int RW, int PRO, int EPI>
+zb_status launch_gemv3_t(zb_ctx* ctx, GemvArgs& a, cudaStream_t stream) {
+  const int nunits = (EPI == EPI_SILU) ? a.F : (EPI == EPI_QKV) ? a.N / 2 : a.N;
+  const int grid = nunits < ctx->num_sms ? nunits : ctx->num_sms;
+  const int KS = a.K / (NC * 256);
+  ZB_REQUIRE(ctx, KS >= 1 && KS <= kW3 && kW3 % KS == 0, "gemv3: K=%d does not fit the warp layout", a.K);
+  const int RPS = (kW3 / KS) * RW, stage_bytes = RPS * a.K * 2;
+  static const int ring_kb = env_int("ZB_GEMV_RING_KB", 96);      // two CTAs per SM: this kernel + its PDL successor
+  static const int ahead = env_int("ZB_GEMV_L2_AHEAD", 0);
+  int stages = ring_kb * 1024 / stage_bytes;
+  if (stages < 2) stages = 2;
+  if (stages > kMaxStages) stages = kMaxStages;
+  a.ring_stages = stages; a.prefetch_ahead = ahead;
+  const int nrows_max = ((nunits + grid - 1) / grid) * ((EPI == EPI_SILU || EPI == EPI_QKV) ? 2 : 1);
+  const int nrows_pad = (nrows_max + RPS - 1) / RPS * RPS;
+  const size_t smem = (size_t)stages * stage_bytes + (size_t)nrows_pad * KS * R * sizeof(float);
+  ZB_REQUIRE(ctx, smem <= 220 * 1024, "gemv3: %zu bytes of shared memory", smem);
+  static size_t attr = 0;
+  if (smem > attr) {
+    ZB_CUDA(ctx, cudaFuncSetAttribute(gemv3_kernel<R, NC, RW, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  ZB_CUDA(ctx, zb_launch_pdl(gemv3_kernel<R, NC, RW, PRO, EPI>, dim3(grid), dim3((kW3 + 1) * 32), smem, stream, a));
+  ctx->launches++;
+  return ZB_OK;
+}
+
+// warp layout per K (16 consumer warps = KS k-slices x RG row groups; a stage holds RPS = RG*RW rows):
+//   K=8192: NC=2 KS=16 RG=1 | K=4096: NC=1 KS=16 RG=1 | K=2048: NC=1 KS=8 RG=2
+//   K=1024: NC=1 KS=4 RG=4  | K=512:  NC=1 KS=2  RG=8 | K=256:  NC=1 KS=1 RG=16
+// RW (rows per warp per stage) sets the stage size: K=2048: RW 4/2/1 -> 32/16/8 KB; K=8192: RW 2/1 -> 32/16 KB.
+// Measured on B200 (scripts/sweep_gemv.sh): 32 KB stages are fastest (per-stage barrier + reduction cost dominates).
+template <int R, int PRO, int EPI>
+zb_status launch_gemv3_r(zb_ctx* ctx, GemvArgs& a, cudaStream_t stream) {
+  static const int stage_kb = env_int("ZB_GEMV_STAGE_KB", 32);
+  if (a.K == 8192) {
+    if (stage_kb <= 16) return launch_gemv3_t<R, 2, 1, PRO, EPI>(ctx, a, stream);
+    return launch_gemv3_t<R, 2, 2, PRO, EPI>(ctx, a, stream);
+  }
+  if (stage_kb <= 8) return launch_gemv3_t<R, 1, 1, PRO, EPI>(ctx, a, stream);
+  if (stage_kb <= 16) return launch_gemv3_t<R, 1, 2, PRO, EPI>(ctx, a, stream);
+  return launch_gemv3_t<R, 1, 4, PRO, EPI>(ctx, a, stream);
+}
+
+inline bool gemv3_ok(int K, int N, int epi) {
+  if (K != 256 && K != 512 && K != 1024 && K != 2048 && K != 4096 && K != 8192) return false;
+  if (epi == EPI_QKV && (N & 1)) return false;
+  return true;
 }
 
 template <int PRO, int EPI>
@@ -479,8 +777,10 @@ zb_status launch_gemv(zb_ctx* ctx, GemvArgs& a, cudaStream_t stream) {
   const bool pairs = (EPI == EPI_HEADS && a.cfg_scale != 1.0f);
   const int rows = pairs ? 2 * a.B : a.M;
   ZB_REQUIRE(ctx, a.K % 8 == 0, "gemv: K=%d must be a multiple of 8", a.K);
-  if (rows <= 2) return launch_gemv_t<2, PRO, EPI>(ctx, a, 1, stream);
-  if (rows <= 4) return launch_gemv_t<4, PRO, EPI>(ctx, a, 1, stream);
+  if (rows <= 4 && gemv3_ok(a.K, a.N, EPI) && (!pairs || rows == a.M)) {       // decode: whole batch in registers
+    if (rows <= 2) return launch_gemv3_r<2, PRO, EPI>(ctx, a, stream);
+    return launch_gemv3_r<4, PRO, EPI>(ctx, a, stream);
+  }
   const int mt = kMaxMT;
   const int tiles = pairs ? (a.B + mt / 2 - 1) / (mt / 2) : (a.M + mt - 1) / mt;
   return launch_gemv_t<kMaxMT, PRO, EPI>(ctx, a, tiles, stream);
@@ -503,8 +803,8 @@ zb_status zb_launch_embed(zb_ctx* ctx, const zb_embed_launch& L, cudaStream_t st
   for (int k = 0; k < d.n_codebooks; ++k) a.tab[k] = (const bf16*)L.model->emb[k];
   a.codes = L.codes; a.sb = L.sb; a.sq = L.sq; a.st = L.st; a.B = L.B; a.T = L.T; a.Q = d.n_codebooks; a.D = d.d_model;
   a.vocab = d.emb_vocab; a.repeat = L.repeat; a.out = L.out; a.out_rs = L.out_rs; a.loop = L.loop; a.T_delayed = L.T_delayed;
-  embed_kernel<<<L.B * L.T, 256, 0, stream>>>(a);
-  ZB_CHECK_LAUNCH(ctx);
+  ZB_CUDA(ctx, zb_launch_pdl(embed_kernel, dim3(L.B * L.T), dim3(256), 0, stream, a));
+  ctx->launches++;
   return ZB_OK;
 }
 
@@ -551,8 +851,8 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
       at.scale = 1.0f / sqrtf((float)d.head_dim); at.part = s.part; at.counters = s.counters; at.y = s.attn_y;
       at.loop = loop; at.T_delayed = T_delayed;
       dim3 grid(M, d.n_heads_kv, nsplit);
-      attn_kernel<<<grid, 32 * G, 0, stream>>>(at);
-      ZB_CHECK_LAUNCH(ctx);
+      ZB_CUDA(ctx, zb_launch_pdl(attn_kernel, grid, dim3(32 * G), 0, stream, at));
+      ctx->launches++;
     }
     // 3. out_proj (x repeats), the last one adds the residual
     const bf16* src = s.attn_y;
@@ -615,31 +915,38 @@ zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden
 }
 
 // ---- diagnostics: launch ONE production kernel on scratch activations (bench.py roofline leg) ----
-extern "C" zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows, zb_stream stream) {
+extern "C" zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows, int32_t iters,
+                                     zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
-  ZB_REQUIRE(ctx, model && layer >= 0 && layer < model->d.n_layer && rows >= 1 && rows <= 8, "zb_bench_kernel: bad arguments");
+  ZB_REQUIRE(ctx, model && layer >= 0 && layer < model->d.n_layer && rows >= 1 && rows <= 8 && iters >= 1, "zb_bench_kernel: bad arguments");
   const zb_model_desc& d = model->d;
-  const zb_layer& L = model->layers[layer];
   const size_t need = zb_backbone_scratch_bytes(model, rows, 1, ZB_PAGE_TOKENS) + (size_t)rows * d.d_model * 2 + 256;
   if (zb_status st = zb_scratch_reserve(ctx, need)) return st;
   Scratch s = carve(model, ctx->scratch, rows, 1, nullptr);
   bf16* x = (bf16*)((char*)ctx->scratch + (ctx->scratch_bytes - (((size_t)rows * d.d_model * 2 + 255) / 256 * 256)));
-  GemvArgs a;
-  memset(&a, 0, sizeof(a));
-  a.M = rows;
-  if (which == 2) {          // norm2 -> fc1 -> value * silu(gate)
-    a.W = (const bf16*)L.fc1; a.x = x; a.ldx = d.d_model; a.N = 2 * d.d_ff; a.K = d.d_model; a.F = d.d_ff;
-    a.nw = (const bf16*)L.norm2_w; a.nb = (const bf16*)L.norm2_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
-    a.y = s.h; a.ldy = d.d_ff;
-    return launch_gemv<PRO_NORM, EPI_SILU>(ctx, a, (cudaStream_t)stream);
-  } else if (which == 3) {   // fc2 + residual
-    a.W = (const bf16*)L.fc2; a.x = s.h; a.ldx = d.d_ff; a.N = d.d_model; a.K = d.d_ff;
-    a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model;
-    return launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, (cudaStream_t)stream);
-  } else if (which == 1) {   // out_proj
-    a.W = (const bf16*)L.out_proj; a.x = s.attn_y; a.ldx = d.n_heads * d.head_dim; a.N = d.d_model; a.K = d.n_heads * d.head_dim;
-    a.y = s.y1; a.ldy = d.d_model;
-    return launch_gemv<PRO_NONE, EPI_STORE>(ctx, a, (cudaStream_t)stream);
+  for (int it = 0; it < iters; ++it) {
+    const zb_layer& L = model->layers[(layer + it) % d.n_layer];      // cycle layers: every launch streams from HBM
+    GemvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = rows;
+    zb_status st;
+    if (which == 2) {          // norm2 -> fc1 -> value * silu(gate)
+      a.W = (const bf16*)L.fc1; a.x = x; a.ldx = d.d_model; a.N = 2 * d.d_ff; a.K = d.d_model; a.F = d.d_ff;
+      a.nw = (const bf16*)L.norm2_w; a.nb = (const bf16*)L.norm2_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
+      a.y = s.h; a.ldy = d.d_ff;
+      st = launch_gemv<PRO_NORM, EPI_SILU>(ctx, a, (cudaStream_t)stream);
+    } else if (which == 3) {   // fc2 + residual
+      a.W = (const bf16*)L.fc2; a.x = s.h; a.ldx = d.d_ff; a.N = d.d_model; a.K = d.d_ff;
+      a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model;
+      st = launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, (cudaStream_t)stream);
+    } else if (which == 1) {   // out_proj
+      a.W = (const bf16*)L.out_proj; a.x = s.attn_y; a.ldx = d.n_heads * d.head_dim; a.N = d.d_model; a.K = d.n_heads * d.head_dim;
+      a.y = s.y1; a.ldy = d.d_model;
+      st = launch_gemv<PRO_NONE, EPI_STORE>(ctx, a, (cudaStream_t)stream);
+    } else {
+      return zb_fail(ctx, ZB_ERR_INVALID, "zb_bench_kernel: unknown kernel id %d", which);
+    }
+    if (st) return st;
   }
-  return zb_fail(ctx, ZB_ERR_INVALID, "zb_bench_kernel: unknown kernel id %d", which);
+  return ZB_OK;
 }

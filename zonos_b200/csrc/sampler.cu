@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int V = a.V, Q = a.Q;
   zb_loop_state* st = a.st;
+  pdl_launch_dependents();
+  pdl_wait();
 
   int offset_new = 0;
   uint64_t draw = a.draw_index;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
     if (!a.first && offset_new >= a.T) {
       if (b == 0 && threadIdx.x == 0) {
         st->offset = offset_new; st->done = 1;
-        if (a.mirror) { a.mirror[0] = offset_new; a.mirror[2] = 1; __threadfence_system(); }
+        if (a.mirror) { a.mirror[0] = offset_new; a.mirror[2] = 1; }
       }
       return;
     }
@@ -361,28 +363,26 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
   if (!st) return;
   __syncthreads();
 
-  // ---- EOS state machine + frame write + counters: one thread per utterance ----
-  if (threadIdx.x == 0) {
-    const int eos = V - 1, mask_tok = V;         // 1024 / 1025
-    long long rem = st->remaining[b];
-    int stop = st->stopping[b];
-    if (!a.first) {
-      if (s_tok[0] == eos) {                      // model.py:483-488
-        rem = min(rem, (long long)Q);
-        stop = 1;
-      }
-      long long eos_idx = min((long long)Q - rem, (long long)(Q - 1));   // model.py:490-491
-      if (stop) {
-        for (int k = 0; k < Q; ++k) {             // tensor_ops.py:193-211
-          if (k < eos_idx) s_tok[k] = mask_tok;
-          else if (k == eos_idx) s_tok[k] = eos;
-        }
-      }
+  // ---- EOS state machine + frame write (lane k <-> codebook k of warp 0), then counters (lane 0) ----
+  if (warp != 0) return;
+  const int eos = V - 1, mask_tok = V;           // 1024 / 1025
+  long long rem = st->remaining[b];
+  int stop = st->stopping[b];
+  if (!a.first && s_tok[0] == eos) {             // model.py:483-488
+    rem = min(rem, (long long)Q);
+    stop = 1;
+  }
+  if (lane < Q) {
+    long long tok = s_tok[lane];
+    if (!a.first && stop) {                      // tensor_ops.py:193-211
+      const long long eos_idx = min((long long)Q - rem, (long long)(Q - 1));   // model.py:490-491
+      if (lane < eos_idx) tok = mask_tok;
+      else if (lane == eos_idx) tok = eos;
     }
-    for (int k = 0; k < Q; ++k) {                 // tensor_ops.py:42-53 (only where == -1)
-      int64_t* cell = a.delayed + ((size_t)b * Q + k) * a.T + offset_new;
-      if (*cell == -1) *cell = s_tok[k];
-    }
+    int64_t* cell = a.delayed + ((size_t)b * Q + lane) * a.T + offset_new;    // tensor_ops.py:42-53 (only where == -1)
+    if (*cell == -1) *cell = tok;
+  }
+  if (lane == 0) {
     const int adv = a.first ? a.prefix_len : 1;  // model.py:430-431 / tensor_ops.py:85-86
     a.lengths[b] += adv;
     a.lengths[a.B + b] += adv;
@@ -390,32 +390,27 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
     st->remaining[b] = rem;
     st->stopping[b] = stop;
     __threadfence();
-    int arrived = atomicAdd(&st->arrive, 1);
+    const int arrived = atomicAdd(&st->arrive, 1);
     if (arrived == a.B - 1) {                     // last utterance of this step closes the step
       st->arrive = 0;
       st->draw_idx += 1;
       if (!a.first) {
         const int step_idx = st->step_idx;
-        st->offset = offset_new;
+        int done = 0, steps = step_idx + 1;       // model.py:506
         bool check = (step_idx % 16 == 15);       // tensor_ops.py:90-103
         if (!check && (step_idx % 8 == 7)) {
           int est = a.B * 10 - (step_idx + 1);    // cpu_step_counter == step_idx + 1
           if (est < 0) est = 0;
           check = est < 5;
         }
-        st->steps = step_idx + 1;                 // model.py:506
-        st->step_idx = step_idx + 1;
         if (check) {
           bool all_done = true;
           for (int bb = 0; bb < a.B; ++bb) all_done = all_done && (((volatile long long*)st->remaining)[bb] <= 0);
-          if (all_done) { st->done = 1; st->steps = step_idx; }   // `break` precedes `step = step_idx + 1`
+          if (all_done) { done = 1; steps = step_idx; }   // `break` precedes `step = step_idx + 1`
         }
+        st->offset = offset_new; st->steps = steps; st->step_idx = step_idx + 1; st->done = done;
+        if (a.mirror) { a.mirror[0] = offset_new; a.mirror[1] = step_idx + 1; a.mirror[3] = steps; a.mirror[2] = done; }
       }
-      if (a.mirror) {
-        a.mirror[0] = st->offset; a.mirror[1] = st->step_idx; a.mirror[3] = st->steps; a.mirror[2] = st->done;
-        __threadfence_system();
-      }
-      __threadfence();
     }
   }
 }
@@ -442,7 +437,7 @@ zb_status zb_launch_sample(zb_ctx* ctx, const zb_sample_launch& L, cudaStream_t 
     ZB_CUDA(ctx, cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  sample_kernel<<<L.B, 32 * L.Q, smem, stream>>>(a);
-  ZB_CHECK_LAUNCH(ctx);
+  ZB_CUDA(ctx, zb_launch_pdl(sample_kernel, dim3(L.B), dim3(32 * L.Q), smem, stream, a));
+  ctx->launches++;
   return ZB_OK;
 }

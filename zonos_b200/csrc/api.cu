@@ -241,8 +241,8 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
   auto fail = [&](zb_status e) { zb_generate_end(g); return e; };
 #define G_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { zb_fail(ctx, ZB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); return fail(ZB_ERR_CUDA); } } while (0)
   G_CUDA(cudaMalloc(&g->st, sizeof(zb_loop_state)));
-  G_CUDA(cudaHostAlloc(&g->st_host, 8 * sizeof(int32_t), cudaHostAllocMapped));
-  memset(g->st_host, 0, 8 * sizeof(int32_t));
+  G_CUDA(cudaHostAlloc(&g->st_host, 16 * sizeof(int32_t), cudaHostAllocMapped));
+  memset(g->st_host, 0, 16 * sizeof(int32_t));
   g->st_host[0] = desc->prefix_audio_len + 1;
   G_CUDA(cudaHostGetDevicePointer((void**)&g->st_host_dev, g->st_host, 0));
   G_CUDA(cudaMalloc(&g->logits, (size_t)B * Q * md.head_vocab * 4));
@@ -313,9 +313,13 @@ zb_status zb_generate_poll(zb_gen* gen, zb_gen_progress* out, zb_stream stream) 
   if (!gen || !out) return ZB_ERR_INVALID;
   zb_ctx* ctx = gen->ctx;
   cudaStream_t s = (cudaStream_t)stream;
+  int32_t* tmp = gen->st_host + 8;                 // second half of the pinned block: staging for an exact read-back
+  ZB_CUDA(ctx, cudaMemcpyAsync(tmp, gen->st, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   ZB_CUDA(ctx, cudaStreamSynchronize(s));
-  zb_generate_peek(gen, out);
-  out->done = out->done || gen->steps_enqueued >= gen->max_steps;
+  out->offset = tmp[0];
+  out->steps = tmp[3];
+  out->max_steps = gen->max_steps;
+  out->done = tmp[2] || gen->steps_enqueued >= gen->max_steps;
   return ZB_OK;
 }
 

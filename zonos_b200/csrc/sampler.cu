@@ -409,7 +409,8 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
           if (all_done) { done = 1; steps = step_idx; }   // `break` precedes `step = step_idx + 1`
         }
         st->offset = offset_new; st->steps = steps; st->step_idx = step_idx + 1; st->done = done;
-        if (a.mirror) { a.mirror[0] = offset_new; a.mirror[1] = step_idx + 1; a.mirror[3] = steps; a.mirror[2] = done; }
+        // host-visible progress (host-mapped memory, PCIe write): only on the steps the host may look at
+        if (a.mirror && (check || done)) { a.mirror[0] = offset_new; a.mirror[1] = step_idx + 1; a.mirror[3] = steps; a.mirror[2] = done; }
       }
     }
   }

@@ -691,6 +691,8 @@ __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
 // ------------------------------------------------------------------ plain norm ---------------
 struct NormArgs { const bf16* x; int64_t ldx; bf16* y; int64_t ldy; const bf16* w; const bf16* b; int D; float eps; int kind; };
 __global__ void __launch_bounds__(256) norm_kernel(NormArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bf16* src = a.x + (size_t)blockIdx.x * a.ldx;
@@ -717,7 +719,7 @@ __global__ void __launch_bounds__(256) norm_kernel(NormArgs a) {
 
 // ------------------------------------------------------------------ host side ----------------
 struct Scratch {
-  bf16 *q, *attn_y, *y1, *h; float* part; int32_t* counters; int nsplit;
+  bf16 *q, *attn_y, *y1, *h, *xn; float* part; int32_t* counters; int nsplit;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -729,12 +731,13 @@ Scratch carve(const zb_model* mdl, void* base, int M, int nsplit, size_t* total)
   const size_t qn = (size_t)d.n_heads * d.head_dim;
   size_t o_q = take((size_t)M * qn * 2), o_ay = take((size_t)M * qn * 2), o_y1 = take((size_t)M * d.d_model * 2);
   size_t o_h = take((size_t)M * d.d_ff * 2);
+  size_t o_xn = take((size_t)M * d.d_model * 2);
   size_t o_part = take((size_t)M * d.n_heads * nsplit * kPart * 4);
   if (total) *total = off;
   Scratch s{};
   if (base) {
     char* b = (char*)base;
-    s.q = (bf16*)(b + o_q); s.attn_y = (bf16*)(b + o_ay); s.y1 = (bf16*)(b + o_y1); s.h = (bf16*)(b + o_h);
+    s.q = (bf16*)(b + o_q); s.attn_y = (bf16*)(b + o_ay); s.y1 = (bf16*)(b + o_y1); s.h = (bf16*)(b + o_h); s.xn = (bf16*)(b + o_xn);
     s.part = (float*)(b + o_part);
   }
   s.nsplit = nsplit;
@@ -871,20 +874,38 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
   const int qn = d.n_heads * d.head_dim;
   const int G = d.n_heads / d.n_heads_kv;
 
+  const bool tc = M > 4 && d.rope_interleaved && d.d_model % 64 == 0 && d.d_ff % 64 == 0;   // dense path: tcgen05 GEMMs
+  auto norm_rows = [&](const bf16* w, const bf16* b) -> zb_status {
+    NormArgs na;
+    na.x = x; na.ldx = d.d_model; na.y = s.xn; na.ldy = d.d_model; na.w = w; na.b = b; na.D = d.d_model; na.eps = d.norm_eps; na.kind = d.norm_kind;
+    ZB_CUDA(ctx, zb_launch_pdl(norm_kernel, dim3(M), dim3(256), 0, stream, na));
+    ctx->launches++;
+    return ZB_OK;
+  };
   for (int li = 0; li < d.n_layer; ++li) {
     const zb_layer& L = model->layers[li];
     ZB_REQUIRE(ctx, L.kind == ZB_LAYER_ATTENTION, "layer %d: only attention layers are implemented in this build", li);
     bf16* kv_layer = (bf16*)cache->kv_pages + (size_t)model->attn_index[li] * cache->num_pages * page_elems;
     GemvArgs a;
     // 1. norm -> in_proj -> RoPE -> KV append (+ q)
-    memset(&a, 0, sizeof(a));
-    a.W = (const bf16*)L.in_proj; a.x = x; a.ldx = d.d_model; a.M = M; a.N = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim; a.K = d.d_model;
-    a.nw = (const bf16*)L.norm_w; a.nb = (const bf16*)L.norm_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
-    a.T = T; a.Hq = d.n_heads; a.Hkv = d.n_heads_kv; a.hd = d.head_dim; a.rope_interleaved = d.rope_interleaved;
-    a.rope = d.rope_table; a.rope_len = d.rope_len; a.lengths = cache->lengths; a.page_table = cache->page_table;
-    a.max_pages = cache->max_pages_per_row; a.num_pages = cache->num_pages; a.kv_layer = kv_layer; a.q_out = s.q;
-    a.loop = loop; a.T_delayed = T_delayed;
-    if (zb_status st = launch_gemv<PRO_NORM, EPI_QKV>(ctx, a, stream)) return st;
+    if (tc) {
+      if (zb_status st = norm_rows((const bf16*)L.norm_w, (const bf16*)L.norm_b)) return st;
+      zb_gemm_tc g;
+      g.W = (const bf16*)L.in_proj; g.x = s.xn; g.ldx = d.d_model; g.M = M; g.N = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim; g.K = d.d_model;
+      g.epi = 2; g.T = T; g.Hq = d.n_heads; g.Hkv = d.n_heads_kv; g.hd = d.head_dim; g.rope_interleaved = d.rope_interleaved;
+      g.rope = d.rope_table; g.rope_len = d.rope_len; g.lengths = cache->lengths; g.page_table = cache->page_table;
+      g.max_pages = cache->max_pages_per_row; g.kv_layer = kv_layer; g.q_out = s.q;
+      if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
+    } else {
+      memset(&a, 0, sizeof(a));
+      a.W = (const bf16*)L.in_proj; a.x = x; a.ldx = d.d_model; a.M = M; a.N = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim; a.K = d.d_model;
+      a.nw = (const bf16*)L.norm_w; a.nb = (const bf16*)L.norm_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
+      a.T = T; a.Hq = d.n_heads; a.Hkv = d.n_heads_kv; a.hd = d.head_dim; a.rope_interleaved = d.rope_interleaved;
+      a.rope = d.rope_table; a.rope_len = d.rope_len; a.lengths = cache->lengths; a.page_table = cache->page_table;
+      a.max_pages = cache->max_pages_per_row; a.num_pages = cache->num_pages; a.kv_layer = kv_layer; a.q_out = s.q;
+      a.loop = loop; a.T_delayed = T_delayed;
+      if (zb_status st = launch_gemv<PRO_NORM, EPI_QKV>(ctx, a, stream)) return st;
+    }
     // 2. attention over the paged cache
     {
       AttnArgs at;
@@ -900,31 +921,49 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
     // 3. out_proj (x repeats), the last one adds the residual
     const bf16* src = s.attn_y;
     for (int rep = 0; rep < d.out_proj_repeats; ++rep) {
-      memset(&a, 0, sizeof(a));
-      a.W = (const bf16*)L.out_proj; a.x = src; a.ldx = qn; a.M = M; a.N = d.d_model; a.K = qn;
-      a.loop = loop; a.T_delayed = T_delayed;
-      if (rep == d.out_proj_repeats - 1) {
-        a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model;
-        if (zb_status st = launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, stream)) return st;
+      const bool last = rep == d.out_proj_repeats - 1;
+      bf16* dst = last ? x : ((src == s.y1) ? s.attn_y : s.y1);
+      if (!last) ZB_REQUIRE(ctx, qn == d.d_model, "out_proj_repeats > 1 needs H*hd == D");
+      if (tc) {
+        zb_gemm_tc g;
+        g.W = (const bf16*)L.out_proj; g.x = src; g.ldx = qn; g.M = M; g.N = d.d_model; g.K = qn;
+        g.epi = last ? 1 : 0; g.y = dst; g.ldy = d.d_model; g.resid = x; g.ldr = d.d_model;
+        if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
       } else {
-        ZB_REQUIRE(ctx, qn == d.d_model, "out_proj_repeats > 1 needs H*hd == D");
-        bf16* dst = (src == s.y1) ? s.attn_y : s.y1;
-        a.y = dst; a.ldy = d.d_model;
-        if (zb_status st = launch_gemv<PRO_NONE, EPI_STORE>(ctx, a, stream)) return st;
-        src = dst;
+        memset(&a, 0, sizeof(a));
+        a.W = (const bf16*)L.out_proj; a.x = src; a.ldx = qn; a.M = M; a.N = d.d_model; a.K = qn;
+        a.loop = loop; a.T_delayed = T_delayed; a.y = dst; a.ldy = d.d_model;
+        if (last) {
+          a.resid = x; a.ldr = d.d_model;
+          if (zb_status st = launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, stream)) return st;
+        } else {
+          if (zb_status st = launch_gemv<PRO_NONE, EPI_STORE>(ctx, a, stream)) return st;
+        }
       }
+      src = dst;
     }
-    // 4. norm2 -> fc1 -> value * silu(gate)
-    memset(&a, 0, sizeof(a));
-    a.W = (const bf16*)L.fc1; a.x = x; a.ldx = d.d_model; a.M = M; a.N = 2 * d.d_ff; a.K = d.d_model; a.F = d.d_ff;
-    a.nw = (const bf16*)L.norm2_w; a.nb = (const bf16*)L.norm2_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
-    a.y = s.h; a.ldy = d.d_ff; a.loop = loop; a.T_delayed = T_delayed;
-    if (zb_status st = launch_gemv<PRO_NORM, EPI_SILU>(ctx, a, stream)) return st;
-    // 5. fc2 + residual
-    memset(&a, 0, sizeof(a));
-    a.W = (const bf16*)L.fc2; a.x = s.h; a.ldx = d.d_ff; a.M = M; a.N = d.d_model; a.K = d.d_ff;
-    a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model; a.loop = loop; a.T_delayed = T_delayed;
-    if (zb_status st = launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, stream)) return st;
+    // 4. norm2 -> fc1 -> value * silu(gate)      5. fc2 + residual
+    if (tc) {
+      if (zb_status st = norm_rows((const bf16*)L.norm2_w, (const bf16*)L.norm2_b)) return st;
+      zb_gemm_tc g;
+      g.W = (const bf16*)L.fc1; g.x = s.xn; g.ldx = d.d_model; g.M = M; g.N = 2 * d.d_ff; g.K = d.d_model; g.F = d.d_ff;
+      g.epi = 3; g.y = s.h; g.ldy = d.d_ff;
+      if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
+      zb_gemm_tc g2;
+      g2.W = (const bf16*)L.fc2; g2.x = s.h; g2.ldx = d.d_ff; g2.M = M; g2.N = d.d_model; g2.K = d.d_ff;
+      g2.epi = 1; g2.y = x; g2.ldy = d.d_model; g2.resid = x; g2.ldr = d.d_model;
+      if (zb_status st = zb_launch_gemm_tc(ctx, g2, stream)) return st;
+    } else {
+      memset(&a, 0, sizeof(a));
+      a.W = (const bf16*)L.fc1; a.x = x; a.ldx = d.d_model; a.M = M; a.N = 2 * d.d_ff; a.K = d.d_model; a.F = d.d_ff;
+      a.nw = (const bf16*)L.norm2_w; a.nb = (const bf16*)L.norm2_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
+      a.y = s.h; a.ldy = d.d_ff; a.loop = loop; a.T_delayed = T_delayed;
+      if (zb_status st = launch_gemv<PRO_NORM, EPI_SILU>(ctx, a, stream)) return st;
+      memset(&a, 0, sizeof(a));
+      a.W = (const bf16*)L.fc2; a.x = s.h; a.ldx = d.d_ff; a.M = M; a.N = d.d_model; a.K = d.d_ff;
+      a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model; a.loop = loop; a.T_delayed = T_delayed;
+      if (zb_status st = launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, stream)) return st;
+    }
   }
   return ZB_OK;
 }

@@ -1,0 +1,333 @@
+// tcgen05 / TMEM GEMM for the dense contractions of the path (prefill, decode with more than 4 activation rows):
+//     Y[M, N] = X[M, K] * W[N, K]^T        bf16 operands, fp32 accumulation in tensor memory
+// "Swap-AB" tiling: the 128 MMA rows are WEIGHT rows (a CTA owns 128 output features and streams their K-major
+// rows once), the MMA N dimension is a block of BN <= 256 activation rows, so one UMMA shape serves M = 8 ... 256+
+// activation rows and the accumulator D[feature, row] lives in 128 lanes x BN columns of TMEM.
+//   warp 4   : TMA producer  (cp.async.bulk.tensor.2d, 128-byte swizzle, mbarrier complete_tx)
+//   warp 5   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, cta_group::1, UMMA 128 x BN x 16)
+//   warps 0-3: epilogue: tcgen05.ld 32 lanes x 16 columns -> registers -> fused epilogue (same rounding points as
+//              the GEMV path: bf16 Linear output, then residual / SiLU gate / RoPE + paged KV append / fp32 CFG mix)
+// SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA).
+#include <cuda.h>
+
+#include "internal.h"
+
+namespace {
+
+constexpr int TC_BM = 128;        // weight rows per CTA (UMMA M)
+constexpr int TC_BK = 64;         // k per stage: 64 bf16 = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+enum { TEPI_STORE = 0, TEPI_RESID = 1, TEPI_QKV = 2, TEPI_SILU = 3, TEPI_HEADS = 4 };
+
+struct TcArgs {
+  CUtensorMap map_w;    // weights  [N, K], box {64 k, 64 rows}
+  CUtensorMap map_x;    // activations [M, K], box {64 k, BN rows}
+  int M, N, K, BN, stages, epi;
+  int F;                // SILU: value rows [0,F), gate rows [F,2F)
+  bf16* y; long long ldy; const bf16* resid; long long ldr;
+  // QKV
+  int T, Hq, Hkv, hd, rope_interleaved, rope_len, max_pages;
+  const float* rope; const int32_t* lengths; const int32_t* page_table; bf16* kv_layer; bf16* q_out;
+  // HEADS
+  int B; float cfg_scale; float* logits; int QV;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (bf16 in, fp32 accumulate)
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 columns of fp32 -> 16 registers per thread (thread t of the warp <-> TMEM lane base+t)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1 |
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6), a/b format BF16 = 1 @ [7,10)/[10,13),
+// a/b major K = 0 @ 15/16, N >> 3 @ [17,23), M >> 4 @ [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcArgs a) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(1024) unsigned char smem_tc[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = a.BN;
+  const int a_bytes = TC_BM * TC_BK * 2;                 // 16 KB
+  const int b_bytes = BN * TC_BK * 2;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) / 1024) * 1024;
+  // 1024-byte aligned base (swizzle atoms)
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_tc) + 1023) & ~(uintptr_t)1023);
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  const int m0 = m_tile * BN;
+  // weight rows of this tile: two 64-row halves (SILU: value rows | gate rows)
+  int row_lo, row_hi;
+  if (a.epi == TEPI_SILU) { row_lo = n_tile * 64; row_hi = a.F + n_tile * 64; }
+  else { row_lo = n_tile * TC_BM; row_hi = row_lo + 64; }
+  const int nk = a.K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < BN) ncols <<= 1;
+  if (warp == 5) {                                       // TMEM allocation by one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % a.stages;
+        if (kb >= a.stages) mbar_wait(&empty_bar[s], ((kb / a.stages) - 1) & 1);
+        unsigned char* sa = base + (size_t)s * stage_bytes;
+        unsigned char* sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
+        tma_load_2d(sa, &a.map_w, kb * TC_BK, row_lo, &full_bar[s]);
+        tma_load_2d(sa + a_bytes / 2, &a.map_w, kb * TC_BK, row_hi, &full_bar[s]);
+        tma_load_2d(sb, &a.map_x, kb * TC_BK, m0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TC_BM, BN);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % a.stages;
+        mbar_wait(&full_bar[s], (kb / a.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 16; ++kk)          // UMMA K = 16 bf16 = 32 bytes: advance the start address
+          tc_mma(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+        tc_commit(&empty_bar[s]);                        // frees the smem slot when these MMAs retire
+      }
+      tc_commit(&tmem_full_bar);                         // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32) = weight rows of the tile =====
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const int lr = warp * 32 + lane;                                   // row inside the 128-row tile
+    const int n = (lr < 64) ? row_lo + lr : row_hi + (lr - 64);        // weight row == output feature
+    const bool n_ok = n < a.N;
+    float* xchg = reinterpret_cast<float*>(base);                      // SILU: gate values [64][BN] (ring is idle now)
+    if (a.epi == TEPI_SILU) {
+      // pass 1: gate rows (warps 2,3) park their bf16-rounded values in shared memory
+      if (warp >= 2) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xchg[(size_t)(lr - 64) * BN + c0 + j] = rbf(v[j]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp < 2) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + c0 + j;
+            if (m < a.M && n_ok) {
+              const float g = xchg[(size_t)lr * BN + c0 + j];
+              const float sg = rbf(g / (1.0f + expf(-g)));
+              a.y[(size_t)m * a.ldy + n] = f2bf(__fmul_rn(rbf(v[j]), sg));
+            }
+          }
+        }
+      }
+    } else {
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        if (a.epi == TEPI_HEADS && a.cfg_scale != 1.0f) {
+          // columns [0,B) are cond rows, [B,2B) uncond rows (single m tile): park the bf16-rounded row in shared memory
+          // (the ring is idle now) and mix in a second pass, so no unaligned TMEM column reads are needed
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xchg[(size_t)lr * BN + c0 + j] = rbf(v[j]);
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int m = m0 + c0 + j;
+          const float val = v[j];
+          if (a.epi == TEPI_QKV) {
+            // RoPE pairs (2i, 2i+1) sit in adjacent lanes (interleaved convention, _torch.py:57-68)
+            const float other = __shfl_xor_sync(0xffffffffu, rbf(val), 1);
+            if (m < a.M && n_ok) {
+              const int r = m / a.T, t = m % a.T;
+              const int pos = a.lengths[r] + t;
+              const int qn = a.Hq * a.hd, kn = a.Hkv * a.hd;
+              float o = rbf(val);
+              if (n < qn + kn) {
+                const int i = (n % a.hd) / 2;
+                const float2 cs = *reinterpret_cast<const float2*>(a.rope + ((size_t)min(pos, a.rope_len - 1) * (a.hd / 2) + i) * 2);
+                o = (n & 1) ? __fadd_rn(__fmul_rn(o, cs.x), __fmul_rn(other, cs.y))      // x1*c + x0*s
+                            : __fsub_rn(__fmul_rn(o, cs.x), __fmul_rn(other, cs.y));     // x0*c - x1*s
+              }
+              if (n < qn) {
+                a.q_out[(size_t)m * qn + n] = f2bf(o);
+              } else {
+                const int kvsel = n < qn + kn ? 0 : 1;
+                const int ci = n - qn - kvsel * kn;
+                const int page = a.page_table[(size_t)r * a.max_pages + pos / ZB_PAGE_TOKENS];
+                bf16* pb = a.kv_layer + ((size_t)page * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
+                pb[((size_t)(ci / a.hd) * ZB_PAGE_TOKENS + pos % ZB_PAGE_TOKENS) * a.hd + (ci % a.hd)] = f2bf(o);
+              }
+            }
+          } else if (m < a.M && n_ok) {
+            if (a.epi == TEPI_STORE) a.y[(size_t)m * a.ldy + n] = f2bf(val);
+            else if (a.epi == TEPI_RESID) a.y[(size_t)m * a.ldy + n] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n]) + rbf(val));
+            else if (a.epi == TEPI_HEADS) a.logits[(size_t)m * a.QV + n] = rbf(val);
+          }
+        }
+      }
+    }
+    if (a.epi == TEPI_HEADS && a.cfg_scale != 1.0f && n_ok) {
+      for (int b = 0; b < a.B; ++b) {                      // u + (c - u) * s in fp32 (model.py:230-232)
+        const float cc = xchg[(size_t)lr * BN + b], uu = xchg[(size_t)lr * BN + a.B + b];
+        a.logits[(size_t)b * a.QV + n] = __fadd_rn(uu, __fmul_rn(__fsub_rn(cc, uu), a.cfg_scale));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ---------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] (cols contiguous), box {64 cols, box_rows}, 128-byte swizzle, zero fill out of bounds
+zb_status make_map_2d(zb_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  ZB_REQUIRE(ctx, enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ZB_REQUIRE(ctx, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%llu x %llu] ld %llu box %u", (int)r, (unsigned long long)rows,
+             (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+  return ZB_OK;
+}
+
+}  // namespace
+
+// Y = X W^T with a fused epilogue.  X rows must be 16-byte aligned and K a multiple of 64.
+zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t stream) {
+  ZB_REQUIRE(ctx, g.K % TC_BK == 0 && g.K >= TC_BK, "gemm_tc: K=%d must be a multiple of 64", g.K);
+  ZB_REQUIRE(ctx, g.M >= 1 && g.N >= 1, "gemm_tc: empty problem");
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  // activation rows per tile: a multiple of 16, at most 256, balanced over the tiles
+  int mtiles = (g.M + 255) / 256;
+  int BN = ((g.M + mtiles - 1) / mtiles + 15) / 16 * 16;
+  if (g.epi == TEPI_HEADS && g.cfg_scale != 1.0f) {
+    ZB_REQUIRE(ctx, g.M <= 256, "gemm_tc: CFG heads need all rows in one tile (M=%d)", g.M);
+    mtiles = 1;
+    BN = (g.M + 15) / 16 * 16;
+  }
+  if (BN < 16) BN = 16;
+  a.M = g.M; a.N = g.N; a.K = g.K; a.BN = BN; a.epi = g.epi; a.F = g.F;
+  a.y = g.y; a.ldy = g.ldy; a.resid = g.resid; a.ldr = g.ldr;
+  a.T = g.T; a.Hq = g.Hq; a.Hkv = g.Hkv; a.hd = g.hd; a.rope_interleaved = g.rope_interleaved; a.rope_len = g.rope_len;
+  a.max_pages = g.max_pages; a.rope = g.rope; a.lengths = g.lengths; a.page_table = g.page_table; a.kv_layer = g.kv_layer; a.q_out = g.q_out;
+  a.B = g.B; a.cfg_scale = g.cfg_scale; a.logits = g.logits; a.QV = g.QV;
+  ZB_REQUIRE(ctx, g.epi != TEPI_QKV || g.rope_interleaved, "gemm_tc: rotate-half RoPE epilogue is not implemented");
+  if (zb_status st = make_map_2d(ctx, &a.map_w, g.W, g.N, g.K, g.K, 64)) return st;
+  if (zb_status st = make_map_2d(ctx, &a.map_x, g.x, g.M, g.K, g.ldx, BN)) return st;
+  const int a_bytes = TC_BM * TC_BK * 2, b_bytes = ((BN * TC_BK * 2 + 1023) / 1024) * 1024;
+  int stages = (200 * 1024) / (a_bytes + b_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  size_t smem = (size_t)stages * (a_bytes + b_bytes) + 1024;
+  if ((size_t)128 * BN * 4 + 1024 > smem) smem = (size_t)128 * BN * 4 + 1024;     // epilogue exchange buffer reuses the ring
+  static size_t attr = 0;
+  if (smem > attr) {
+    ZB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int ntiles = (g.epi == TEPI_SILU) ? (g.F + 63) / 64 : (g.N + TC_BM - 1) / TC_BM;
+  ZB_CUDA(ctx, zb_launch_pdl(gemm_tc_kernel, dim3(ntiles, mtiles), dim3(TC_THREADS), smem, stream, a));
+  ctx->launches++;
+  return ZB_OK;
+}
+
+// diagnostics: plain Y = X W^T (bf16) for tests
+extern "C" ZB_API zb_status zb_debug_gemm(zb_ctx* ctx, const void* x, const void* w, void* y, int32_t M, int32_t N, int32_t K, zb_stream stream) {
+  if (!ctx) return ZB_ERR_INVALID;
+  zb_gemm_tc g;
+  g.W = (const bf16*)w; g.x = (const bf16*)x; g.ldx = K; g.M = M; g.N = N; g.K = K; g.epi = TEPI_STORE; g.y = (bf16*)y; g.ldy = N;
+  return zb_launch_gemm_tc(ctx, g, (cudaStream_t)stream);
+}

@@ -61,4 +61,16 @@ zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden
                           cudaStream_t stream);
 size_t zb_backbone_scratch_bytes(const zb_model* model, int R, int T, int max_kv_len);
 
+// ---- tcgen05 GEMM (gemm_tc.cu): Y[M,N] = X[M,K] W[N,K]^T with fused epilogue ----
+struct zb_gemm_tc {
+  const bf16* W = nullptr; const bf16* x = nullptr; long long ldx = 0; int M = 0, N = 0, K = 0;
+  int epi = 0;                 // 0 store, 1 +residual, 2 QKV (RoPE + KV append), 3 SiLU gate, 4 heads (fp32 logits, CFG mix)
+  int F = 0;
+  bf16* y = nullptr; long long ldy = 0; const bf16* resid = nullptr; long long ldr = 0;
+  int T = 1, Hq = 0, Hkv = 0, hd = 0, rope_interleaved = 1, rope_len = 0, max_pages = 0;
+  const float* rope = nullptr; const int32_t* lengths = nullptr; const int32_t* page_table = nullptr; bf16* kv_layer = nullptr; bf16* q_out = nullptr;
+  int B = 0; float cfg_scale = 1.0f; float* logits = nullptr; int QV = 0;
+};
+zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t stream);
+
 // ---- DAC (dac.cu) ----

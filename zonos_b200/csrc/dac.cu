@@ -12,9 +12,11 @@
 // elementwise kernel ever touches HBM.  The 9 codebook lookups + 1x1 projections are one gather-sum over a
 // table precomputed at create time.  Numerics follow the reference's CUDA autocast path: bf16 conv operands,
 // fp32 accumulation, fp32 Snake, bf16 residual stream.
+#include <stdlib.h>
+
 #include <algorithm>
 
-#include "internal.h"
+#include "tc.cuh"
 
 namespace {
 
@@ -23,9 +25,10 @@ struct ConvArgs {
   const bf16* w;       // [taps][N][Cin]
   const float* bias;   // [Cout]
   int B, Lin, Cin, Cout, N, taps, dil, pad, ups, rows, Lout;
-  const bf16* resid;   // [B][Lout][Cout] or null
-  bf16* out_raw;       // [B][Lout][Cout] or null
-  bf16* out_act;       // [B][Lout][Cout] or null: snake(out, alpha)
+  int in_ld, out_ld;   // channel strides (channels padded to a multiple of 64 for the 128-byte-swizzled TMA boxes)
+  const bf16* resid;   // [B][Lout][out_ld] or null
+  bf16* out_raw;       // [B][Lout][out_ld] or null
+  bf16* out_act;       // [B][Lout][out_ld] or null: snake(out, alpha)
   const float* alpha;  // [Cout] or null (identity)
 };
 
@@ -48,23 +51,23 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(ConvArgs a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const bf16* inb = a.in + (size_t)b * a.Lin * a.Cin;
+  const bf16* inb = a.in + (size_t)b * a.Lin * a.in_ld;
   for (int tap = 0; tap < a.taps; ++tap) {
     const int shift = a.ups ? -tap : tap * a.dil - a.pad;
-    const bf16* wt = a.w + (size_t)tap * a.N * a.Cin;
-    for (int c0 = 0; c0 < a.Cin; c0 += BK) {
+    const bf16* wt = a.w + (size_t)tap * a.N * a.in_ld;
+    for (int c0 = 0; c0 < a.in_ld; c0 += BK) {
       // A tile: 64 rows x 32 channels, B tile: 64 cols x 32 channels (8 bf16 per thread each)
       {
         const int row = threadIdx.x / 4, c8 = (threadIdx.x % 4) * 8;
         const int jj = j0 + row + shift;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (jj >= 0 && jj < a.Lin && j0 + row < a.rows) v = *reinterpret_cast<const uint4*>(inb + (size_t)jj * a.Cin + c0 + c8);
+        if (jj >= 0 && jj < a.Lin && j0 + row < a.rows) v = *reinterpret_cast<const uint4*>(inb + (size_t)jj * a.in_ld + c0 + c8);
         const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) { As[c8 + 2 * q][row] = bf16lo(w4[q]); As[c8 + 2 * q + 1][row] = bf16hi(w4[q]); }
         const int n = n0 + row;
         uint4 u = make_uint4(0, 0, 0, 0);
-        if (n < a.N) u = *reinterpret_cast<const uint4*>(wt + (size_t)n * a.Cin + c0 + c8);
+        if (n < a.N) u = *reinterpret_cast<const uint4*>(wt + (size_t)n * a.in_ld + c0 + c8);
         const uint32_t u4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) { Bs[c8 + 2 * q][row] = bf16lo(u4[q]); Bs[c8 + 2 * q + 1][row] = bf16hi(u4[q]); }
@@ -95,12 +98,164 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(ConvArgs a) {
       int time = j, co = n;
       if (a.ups) { const int ph = n / a.Cout; co = n % a.Cout; time = a.ups * j + ph - a.pad; }
       if (time < 0 || time >= a.Lout) continue;
-      const size_t o = ((size_t)b * a.Lout + time) * a.Cout + co;
+      const size_t o = ((size_t)b * a.Lout + time) * a.out_ld + co;
       float v = rbf(acc[i][jj] + a.bias[co]);                       // conv output is bf16 under autocast
       if (a.resid) v = rbf(bf2f(a.resid[o]) + v);                   // bf16 residual add (modeling_dac.py:206)
       if (a.out_raw) a.out_raw[o] = f2bf(v);
       if (a.out_act) a.out_act[o] = f2bf(a.alpha ? snake_f(v, a.alpha[co]) : v);
     }
+  }
+}
+
+
+// ------------------------------------------------------------------ tcgen05 implicit-GEMM convolution ---------
+// D[128 time rows x BN output columns] (TMEM) = sum_tap sum_cin-chunk A_tap[128 x 64] * W_tap[BN x 64]^T.
+// A is fetched by a 3-D TMA box {64 channels, 128 time steps, 1 batch} at time offset j0 + shift(tap): rows outside
+// [0, Lin) are zero-filled by the TMA unit, which IS the convolution's zero padding (per batch element).
+//   warp 4: TMA producer | warp 5: TMEM alloc + tcgen05.mma issuer | warps 0-3: epilogue (lane <-> time row)
+constexpr int CV_THREADS = 192;
+struct ConvTcArgs {
+  CUtensorMap map_in;   // activations [B][Lin][in_ld], box {64, 128, 1}
+  CUtensorMap map_w;    // weights [taps*N][in_ld], box {64, BN}
+  ConvArgs c;
+  int BN, stages;
+};
+
+__global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs p) {
+  extern __shared__ __align__(1024) unsigned char smem_cv[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const ConvArgs& a = p.c;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  const int a_bytes = 128 * 64 * 2, b_bytes = BN * 64 * 2;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) / 1024) * 1024;
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_cv) + 1023) & ~(uintptr_t)1023);
+  const int j0 = blockIdx.x * 128, n0 = blockIdx.y * BN, b = blockIdx.z;
+  const int kchunks = a.in_ld / 64;
+  const int nk = a.taps * kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < BN) ncols <<= 1;
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % p.stages;
+        if (kb >= p.stages) mbar_wait(&empty_bar[s], ((kb / p.stages) - 1) & 1);
+        const int tap = kb / kchunks, c0 = (kb % kchunks) * 64;
+        const int shift = a.ups ? -tap : tap * a.dil - a.pad;
+        unsigned char* sa = base + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
+        tma_load_3d(sa, &p.map_in, c0, j0 + shift, b, &full_bar[s]);
+        tma_load_2d(sa + a_bytes, &p.map_w, c0, tap * a.N + n0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, BN);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(&full_bar[s], (kb / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) tc_mma(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(&tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: lane <-> GEMM row j (time), 16 output columns per TMEM read =====
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const int j = j0 + warp * 32 + lane;
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+      const int nb = n0 + c0;
+      if (j >= a.rows || nb >= a.N) continue;
+      // the 16 columns share one output row when they do not straddle a phase boundary (always true for plain convs)
+      int time = j, co0 = nb;
+      if (a.ups) { const int ph = nb / a.Cout; co0 = nb % a.Cout; time = a.ups * j + ph - a.pad; }
+      const bool same_row = !a.ups || (co0 + 16 <= a.Cout);
+      if (same_row && co0 + 16 <= a.Cout) {
+        if (time < 0 || time >= a.Lout) continue;
+        const size_t o = ((size_t)b * a.Lout + time) * a.out_ld + co0;
+        float r[16];
+        if (a.resid) {
+          const uint4 r0 = *reinterpret_cast<const uint4*>(a.resid + o), r1 = *reinterpret_cast<const uint4*>(a.resid + o + 8);
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { r[2 * q] = bf16lo(rw[q]); r[2 * q + 1] = bf16hi(rw[q]); }
+        }
+        uint32_t raw[8], act[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float x0 = rbf(v[2 * q] + a.bias[co0 + 2 * q]), x1 = rbf(v[2 * q + 1] + a.bias[co0 + 2 * q + 1]);
+          if (a.resid) { x0 = rbf(r[2 * q] + x0); x1 = rbf(r[2 * q + 1] + x1); }
+          raw[q] = pack_bf16(x0, x1);
+          act[q] = a.alpha ? pack_bf16(snake_f(x0, a.alpha[co0 + 2 * q]), snake_f(x1, a.alpha[co0 + 2 * q + 1])) : raw[q];
+        }
+        if (a.out_raw) {
+          *reinterpret_cast<uint4*>(a.out_raw + o) = make_uint4(raw[0], raw[1], raw[2], raw[3]);
+          *reinterpret_cast<uint4*>(a.out_raw + o + 8) = make_uint4(raw[4], raw[5], raw[6], raw[7]);
+        }
+        if (a.out_act) {
+          *reinterpret_cast<uint4*>(a.out_act + o) = make_uint4(act[0], act[1], act[2], act[3]);
+          *reinterpret_cast<uint4*>(a.out_act + o + 8) = make_uint4(act[4], act[5], act[6], act[7]);
+        }
+        // zero the padding channels [Cout, out_ld) once per output row (the thread that owns the last real chunk)
+        if (co0 + 16 == a.Cout && a.out_ld > a.Cout) {
+          for (int cz = a.Cout; cz < a.out_ld; cz += 8) {
+            const size_t oz = ((size_t)b * a.Lout + time) * a.out_ld + cz;
+            if (a.out_raw) *reinterpret_cast<uint4*>(a.out_raw + oz) = make_uint4(0, 0, 0, 0);
+            if (a.out_act) *reinterpret_cast<uint4*>(a.out_act + oz) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int n = nb + q;
+          if (n >= a.N) continue;
+          int t2 = j, co = n;
+          if (a.ups) { const int ph = n / a.Cout; co = n % a.Cout; t2 = a.ups * j + ph - a.pad; }
+          if (t2 < 0 || t2 >= a.Lout) continue;
+          const size_t o = ((size_t)b * a.Lout + t2) * a.out_ld + co;
+          float x0 = rbf(v[q] + a.bias[co]);
+          if (a.resid) x0 = rbf(bf2f(a.resid[o]) + x0);
+          if (a.out_raw) a.out_raw[o] = f2bf(x0);
+          if (a.out_act) a.out_act[o] = f2bf(a.alpha ? snake_f(x0, a.alpha[co]) : x0);
+          if (co == a.Cout - 1 && a.out_ld > a.Cout) {
+            for (int cz = a.Cout; cz < a.out_ld; ++cz) {
+              const size_t oz = ((size_t)b * a.Lout + t2) * a.out_ld + cz;
+              if (a.out_raw) a.out_raw[oz] = f2bf(0.f);
+              if (a.out_act) a.out_act[oz] = f2bf(0.f);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
 
@@ -130,26 +285,26 @@ __global__ void build_table_kernel(const float* E, const float* W, const float* 
 }
 
 // w_out[tap][n][ci] (bf16) from torch Conv1d weight [Cout][Cin][K]
-__global__ void relayout_conv_kernel(const float* w, int Cout, int Cin, int K, bf16* out) {
-  const size_t total = (size_t)K * Cout * Cin;
+__global__ void relayout_conv_kernel(const float* w, int Cout, int Cin, int Cp, int K, bf16* out) {
+  const size_t total = (size_t)K * Cout * Cp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ci = i % Cin; const int co = (i / Cin) % Cout; const int k = i / ((size_t)Cin * Cout);
-    out[i] = f2bf(w[((size_t)co * Cin + ci) * K + k]);
+    const int ci = i % Cp; const int co = (i / Cp) % Cout; const int k = i / ((size_t)Cp * Cout);
+    out[i] = f2bf(ci < Cin ? w[((size_t)co * Cin + ci) * K + k] : 0.f);
   }
 }
 // w_out[tap][ph*Cout+co][ci] from ConvTranspose1d weight [Cin][Cout][2s]; tap 0 <-> k = ph, tap 1 <-> k = ph + s
-__global__ void relayout_convT_kernel(const float* w, int Cin, int Cout, int s, bf16* out) {
-  const size_t total = (size_t)2 * s * Cout * Cin;
+__global__ void relayout_convT_kernel(const float* w, int Cin, int Cp, int Cout, int s, bf16* out) {
+  const size_t total = (size_t)2 * s * Cout * Cp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ci = i % Cin; const size_t r = i / Cin; const int n = r % ((size_t)s * Cout); const int tap = r / ((size_t)s * Cout);
+    const int ci = i % Cp; const size_t r = i / Cp; const int n = r % ((size_t)s * Cout); const int tap = r / ((size_t)s * Cout);
     const int ph = n / Cout, co = n % Cout;
-    out[i] = f2bf(w[((size_t)ci * Cout + co) * (2 * s) + ph + tap * s]);
+    out[i] = f2bf(ci < Cin ? w[((size_t)ci * Cout + co) * (2 * s) + ph + tap * s] : 0.f);
   }
 }
 
 // final Conv1d(C -> 1, k7, pad 3) + tanh  (one warp per output sample)
-__global__ void __launch_bounds__(256) final_conv_kernel(const bf16* in, const bf16* w /*[7][C]*/, const float* bias, int B, int L,
-                                                         int C, float* wav) {
+__global__ void __launch_bounds__(256) final_conv_kernel(const bf16* in, const bf16* w /*[7][ld]*/, const float* bias, int B, int L,
+                                                         int C, int ld, float* wav) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * L) return;
   const int b = warp / L, t = warp % L;
@@ -157,8 +312,8 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const bf16* in, const b
   for (int k = 0; k < 7; ++k) {
     const int tt = t + k - 3;
     if (tt < 0 || tt >= L) continue;
-    const bf16* row = in + ((size_t)b * L + tt) * C;
-    for (int c = lane; c < C; c += 32) s = fmaf(bf2f(row[c]), bf2f(w[k * C + c]), s);
+    const bf16* row = in + ((size_t)b * L + tt) * ld;
+    for (int c = lane; c < C; c += 32) s = fmaf(bf2f(row[c]), bf2f(w[k * ld + c]), s);
   }
   s = warp_sum(s);
   if (lane == 0) wav[(size_t)b * L + t] = tanhf(rbf(s + bias[0]));   // conv out bf16 (autocast); tanh kept in fp32
@@ -166,7 +321,8 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const bf16* in, const b
 
 }  // namespace
 
-struct zb_conv_w { bf16* w = nullptr; float* bias = nullptr; int Cin = 0, Cout = 0, taps = 0, dil = 1, pad = 0, ups = 0; };
+struct zb_conv_w { bf16* w = nullptr; float* bias = nullptr; int Cin = 0, Cinp = 0, Cout = 0, taps = 0, dil = 1, pad = 0, ups = 0; };
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
 struct zb_dac {
   zb_ctx* ctx;
   zb_dac_desc d;
@@ -179,6 +335,8 @@ struct zb_dac {
 };
 
 namespace {
+int env_simt() { const char* v = getenv("ZB_DAC_SIMT"); return v && atoi(v); }
+
 zb_status dev_alloc(zb_dac* d, void** p, size_t bytes) {
   ZB_CUDA(d->ctx, cudaMalloc(p, bytes));
   d->owned.push_back(*p);
@@ -190,30 +348,78 @@ zb_status copy_f32(zb_dac* d, const float* src, size_t n, float** out, cudaStrea
   return ZB_OK;
 }
 zb_status make_conv(zb_dac* d, const float* w, const float* b, int Cout, int Cin, int K, int dil, zb_conv_w* o, cudaStream_t s) {
-  o->Cin = Cin; o->Cout = Cout; o->taps = K; o->dil = dil; o->pad = (K - 1) * dil / 2; o->ups = 0;
-  if (zb_status st = dev_alloc(d, (void**)&o->w, (size_t)K * Cout * Cin * 2)) return st;
-  relayout_conv_kernel<<<256, 256, 0, s>>>(w, Cout, Cin, K, o->w);
+  o->Cin = Cin; o->Cinp = pad64(Cin); o->Cout = Cout; o->taps = K; o->dil = dil; o->pad = (K - 1) * dil / 2; o->ups = 0;
+  if (zb_status st = dev_alloc(d, (void**)&o->w, (size_t)K * Cout * o->Cinp * 2)) return st;
+  relayout_conv_kernel<<<256, 256, 0, s>>>(w, Cout, Cin, o->Cinp, K, o->w);
   ZB_CHECK_LAUNCH(d->ctx);
   return copy_f32(d, b, Cout, &o->bias, s);
 }
 zb_status make_convT(zb_dac* d, const float* w, const float* b, int Cin, int Cout, int stride, zb_conv_w* o, cudaStream_t s) {
-  o->Cin = Cin; o->Cout = Cout; o->taps = 2; o->dil = 1; o->pad = (stride + 1) / 2; o->ups = stride;
-  if (zb_status st = dev_alloc(d, (void**)&o->w, (size_t)2 * stride * Cout * Cin * 2)) return st;
-  relayout_convT_kernel<<<256, 256, 0, s>>>(w, Cin, Cout, stride, o->w);
+  o->Cin = Cin; o->Cinp = pad64(Cin); o->Cout = Cout; o->taps = 2; o->dil = 1; o->pad = (stride + 1) / 2; o->ups = stride;
+  if (zb_status st = dev_alloc(d, (void**)&o->w, (size_t)2 * stride * Cout * o->Cinp * 2)) return st;
+  relayout_convT_kernel<<<256, 256, 0, s>>>(w, Cin, o->Cinp, Cout, stride, o->w);
   ZB_CHECK_LAUNCH(d->ctx);
   return copy_f32(d, b, Cout, &o->bias, s);
+}
+
+zb_status make_map(zb_ctx* ctx, CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  ZB_REQUIRE(ctx, enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ZB_REQUIRE(ctx, r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return ZB_OK;
 }
 
 zb_status run_conv(zb_ctx* ctx, const zb_conv_w& c, const bf16* in, int B, int Lin, const bf16* resid, bf16* out_raw, bf16* out_act,
                    const float* alpha, cudaStream_t s) {
   ConvArgs a;
   a.in = in; a.w = c.w; a.bias = c.bias; a.B = B; a.Lin = Lin; a.Cin = c.Cin; a.Cout = c.Cout; a.taps = c.taps; a.dil = c.dil;
-  a.pad = c.pad; a.ups = c.ups;
+  a.pad = c.pad; a.ups = c.ups; a.in_ld = c.Cinp; a.out_ld = pad64(c.Cout);
   if (c.ups) { a.N = c.ups * c.Cout; a.rows = Lin + 1; a.Lout = Lin * c.ups; }
   else { a.N = c.Cout; a.rows = Lin; a.Lout = Lin; }
   a.resid = resid; a.out_raw = out_raw; a.out_act = out_act; a.alpha = alpha;
-  dim3 grid((a.rows + BM - 1) / BM, (a.N + BN - 1) / BN, B);
-  conv_gemm_kernel<<<grid, 256, 0, s>>>(a);
+  static const int simt = env_simt();
+  if (simt) {
+    dim3 grid((a.rows + BM - 1) / BM, (a.N + BN - 1) / BN, B);
+    conv_gemm_kernel<<<grid, 256, 0, s>>>(a);
+    ZB_CHECK_LAUNCH(ctx);
+    return ZB_OK;
+  }
+  ConvTcArgs p;
+  memset(&p, 0, sizeof(p));
+  p.c = a;
+  // output columns per CTA: a multiple of 16, at most 256, balanced over the tiles
+  const int ntiles = (a.N + 255) / 256;
+  int bn = ((a.N + ntiles - 1) / ntiles + 15) / 16 * 16;
+  p.BN = bn;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.in_ld, (cuuint64_t)Lin, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)a.in_ld * 2, (cuuint64_t)Lin * a.in_ld * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    if (zb_status st = make_map(ctx, &p.map_in, in, 3, dims, str, box)) return st;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.in_ld, (cuuint64_t)c.taps * a.N};
+    cuuint64_t str[1] = {(cuuint64_t)a.in_ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    if (zb_status st = make_map(ctx, &p.map_w, c.w, 2, dims, str, box)) return st;
+  }
+  const int a_bytes = 128 * 64 * 2, b_bytes = ((bn * 64 * 2 + 1023) / 1024) * 1024;
+  int stages = (160 * 1024) / (a_bytes + b_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * (a_bytes + b_bytes) + 1024;
+  static size_t attr = 0;
+  if (smem > attr) {
+    ZB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  dim3 grid((a.rows + 127) / 128, ntiles, B);
+  conv_tc_kernel<<<grid, CV_THREADS, smem, s>>>(p);
   ZB_CHECK_LAUNCH(ctx);
   return ZB_OK;
 }
@@ -285,7 +491,7 @@ extern "C" zb_status zb_dac_decode(zb_ctx* ctx, const zb_dac* dac, const int64_t
   // halving that is the last stage: L = 512 T, C = 96  (and the first: T x 1536 is far smaller)
   int up = 1;
   size_t max_elems = (size_t)T * d.channels;
-  { int ch = d.channels; for (int i = 0; i < d.n_blocks; ++i) { up *= d.strides[i]; ch /= 2; max_elems = std::max(max_elems, (size_t)T * up * ch); } }
+  { int ch = d.channels; for (int i = 0; i < d.n_blocks; ++i) { up *= d.strides[i]; ch /= 2; max_elems = std::max(max_elems, (size_t)T * up * pad64(ch)); } }
   max_elems = std::max(max_elems, (size_t)T * d.latent_dim);
   const size_t buf = (max_elems * B * 2 + 255) / 256 * 256;
   if (zb_status st = zb_dac_scratch_reserve(ctx, 4 * buf)) return st;
@@ -320,7 +526,7 @@ extern "C" zb_status zb_dac_decode(zb_ctx* ctx, const zb_dac* dac, const int64_t
   }
   const int C = dac->conv2.Cin;
   const long long warps = (long long)B * L;
-  final_conv_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(act, dac->conv2.w, dac->conv2.bias, B, L, C, wav);
+  final_conv_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(act, dac->conv2.w, dac->conv2.bias, B, L, C, dac->conv2.Cinp, wav);
   ZB_CHECK_LAUNCH(ctx);
   return ZB_OK;
 }

@@ -181,6 +181,9 @@ struct zb_gen {
   int32_t* st_host_dev = nullptr;   // its device alias
   float* logits = nullptr;          // [B,Q,V]
   bf16* xdec = nullptr;             // [2B, D] residual stream of one decode step
+  void* mega_layers = nullptr;      // device array of per-layer pointers for the persistent decode kernel
+  unsigned* mega_bar = nullptr;     // grid barrier words
+  bool mega = false;
   cudaGraphExec_t graph = nullptr;
   int64_t launches_per_step = 0;
   int max_steps = 0, steps_enqueued = 0, max_kv = 0;
@@ -202,14 +205,20 @@ zb_status enqueue_step(zb_gen* g, cudaStream_t s) {
   zb_embed_launch E;
   E.model = g->model; E.codes = g->d.delayed; E.sb = (int64_t)g->d.Q * g->d.T_delayed; E.sq = g->d.T_delayed; E.st = 1;
   E.B = B; E.T = 1; E.repeat = 2; E.out = g->xdec; E.out_rs = md.d_model; E.loop = g->st; E.T_delayed = g->d.T_delayed;
-  if (zb_status st = zb_launch_embed(ctx, E, s)) return st;
-  if (zb_status st = zb_run_layers(ctx, g->model, &g->cache, g->xdec, R, 1, g->max_kv, g->st, g->d.T_delayed, s)) return st;
-  if (zb_status st = zb_launch_heads(ctx, g->model, g->xdec, md.d_model, R, 1, g->d.cfg_scale, g->logits, g->st, g->d.T_delayed, s)) return st;
+  if (g->mega) {
+    // one cooperative launch: embed + all layers + heads
+    if (zb_status st = zb_launch_decode_step(ctx, g->model, &g->cache, g->mega_layers, g->mega_bar, g->xdec, R, g->max_kv, g->d.cfg_scale, g->logits,
+                                             g->d.delayed, g->d.T_delayed, g->st, s)) return st;
+  } else {
+    if (zb_status st = zb_launch_embed(ctx, E, s)) return st;
+    if (zb_status st = zb_run_layers(ctx, g->model, &g->cache, g->xdec, R, 1, g->max_kv, g->st, g->d.T_delayed, s)) return st;
+    if (zb_status st = zb_launch_heads(ctx, g->model, g->xdec, md.d_model, R, 1, g->d.cfg_scale, g->logits, g->st, g->d.T_delayed, s)) return st;
+  }
   zb_sample_launch L;
   L.logits = g->logits; L.B = B; L.Q = g->d.Q; L.V = md.head_vocab; L.sp = g->d.sampling; L.apply_bias = 1; L.seed = g->d.seed;
   L.st = g->st; L.delayed = g->d.delayed; L.T = g->d.T_delayed; L.ctx_len = g->d.max_new_tokens < 100 ? g->d.max_new_tokens : 100;
   L.lengths = g->cache.lengths; L.q_stream = g->d.q_stream; L.q_calls = g->d.q_calls; L.logits_trace = g->d.logits_trace;
-  L.trace_calls = g->d.trace_calls; L.first = 0; L.mirror = g->st_host_dev;
+  L.trace_calls = g->d.trace_calls; L.first = 0; L.mirror = g->st_host_dev; L.reset_word = g->mega_bar;
   return zb_launch_sample(ctx, L, s);
 }
 }  // namespace
@@ -247,6 +256,16 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
   G_CUDA(cudaHostGetDevicePointer((void**)&g->st_host_dev, g->st_host, 0));
   G_CUDA(cudaMalloc(&g->logits, (size_t)B * Q * md.head_vocab * 4));
   G_CUDA(cudaMalloc(&g->xdec, (size_t)R * md.d_model * 2));
+  g->mega = zb_mega_supported(model, R);
+  if (g->mega) {
+    std::vector<unsigned char> hb(zb_mega_layers_bytes(model));
+    if (zb_status st = zb_mega_layers_build(ctx, model, cache, hb.data())) return fail(st);
+    G_CUDA(cudaMalloc(&g->mega_layers, hb.size()));
+    G_CUDA(cudaMemcpyAsync(g->mega_layers, hb.data(), hb.size(), cudaMemcpyHostToDevice, s));
+    G_CUDA(cudaStreamSynchronize(s));                   // hb is a stack-scoped staging buffer
+    G_CUDA(cudaMalloc(&g->mega_bar, 2 * sizeof(unsigned)));
+    G_CUDA(cudaMemsetAsync(g->mega_bar, 0, 2 * sizeof(unsigned), s));
+  }
   const int offset0 = P + 1;
   g->max_steps = desc->T_delayed - offset0;               // model.py:440
   init_state_kernel<<<1, 256, 0, s>>>(g->st, B, offset0, g->max_steps);
@@ -276,8 +295,9 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
   L.trace_calls = desc->trace_calls; L.first = 1; L.prefix_len = Tp; L.mirror = g->st_host_dev;
   if (zb_status st = zb_launch_sample(ctx, L, s)) return fail(st);
 
-  // ---- capture one loop iteration as a CUDA graph (all positions come from device state) ----
-  {
+  // ---- capture one loop iteration as a CUDA graph (all positions come from device state).  The persistent path is
+  // two launches per step (cooperative step kernel + sampler): no graph needed ----
+  if (!g->mega) {
     const int64_t before = ctx->launches;
     cudaStream_t cs = ctx->capture_stream;
     G_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
@@ -302,8 +322,12 @@ zb_status zb_generate_steps(zb_gen* gen, int32_t n_steps, zb_stream stream) {
   zb_ctx* ctx = gen->ctx;
   cudaStream_t s = (cudaStream_t)stream;
   for (int i = 0; i < n_steps && gen->steps_enqueued < gen->max_steps; ++i) {
-    ZB_CUDA(ctx, cudaGraphLaunch(gen->graph, s));
-    ctx->launches += gen->launches_per_step;
+    if (gen->mega) {
+      if (zb_status st = enqueue_step(gen, s)) return st;
+    } else {
+      ZB_CUDA(ctx, cudaGraphLaunch(gen->graph, s));
+      ctx->launches += gen->launches_per_step;
+    }
     gen->steps_enqueued++;
   }
   return ZB_OK;
@@ -341,6 +365,8 @@ zb_status zb_generate_end(zb_gen* gen) {
   if (gen->st_host) cudaFreeHost(gen->st_host);
   if (gen->logits) cudaFree(gen->logits);
   if (gen->xdec) cudaFree(gen->xdec);
+  if (gen->mega_layers) cudaFree(gen->mega_layers);
+  if (gen->mega_bar) cudaFree(gen->mega_bar);
   delete gen;
   return ZB_OK;
 }

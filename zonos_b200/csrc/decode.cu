@@ -8,6 +8,8 @@
 // Rounding points are the reference's: every Linear / norm / SiLU / residual add rounds to bf16.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "internal.h"
 
 namespace {
@@ -98,6 +100,10 @@ struct GemvArgs {
 };
 
 
+__device__ __forceinline__ float ldcg_bf16(const bf16* p) {
+  return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+
 // Finishes one output pair (n0, n1) of activation row m from the fp32 dot products v0, v1.  Rounding points are the
 // reference's (bf16 Linear output first, then the fused op).  HEADS with CFG: m is the utterance, (v0,v1) its cond
 // row and (u0,u1) its uncond row.
@@ -108,8 +114,8 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, int m, int n0, 
     a.y[(size_t)m * a.ldy + n0] = f2bf(v0);
     if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(v1);
   } else if (EPI == EPI_RESID) {
-    a.y[(size_t)m * a.ldy + n0] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n0]) + rbf(v0));
-    if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n1]) + rbf(v1));
+    a.y[(size_t)m * a.ldy + n0] = f2bf(ldcg_bf16(a.resid + (size_t)m * a.ldr + n0) + rbf(v0));
+    if (has1) a.y[(size_t)m * a.ldy + n1] = f2bf(ldcg_bf16(a.resid + (size_t)m * a.ldr + n1) + rbf(v1));
   } else if (EPI == EPI_SILU) {
     const float yv = rbf(v0), g = rbf(v1);
     const float sg = rbf(g / (1.0f + expf(-g)));            // F.silu on bf16: fp32 math, bf16 result
@@ -688,6 +694,477 @@ __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
   *reinterpret_cast<uint2*>(a.y + (size_t)m * a.Hq * kHD + (size_t)head * kHD + lane * 4) = outv;
 }
 
+
+// ================================================================================================================
+// Persistent decode step: ONE cooperative launch runs embed -> 26 x (in_proj, attention, out_proj x2, fc1, fc2) ->
+// heads for up to 4 activation rows.  148 CTAs (one per SM) stay resident; the phases are separated by grid-wide
+// barriers (consumer warps only), while the producer warp of every CTA streams that CTA's slice of ALL the step's
+// weight matrices back to back through the shared-memory ring - weights do not depend on activations, so HBM keeps
+// streaming across phase boundaries and barrier/LayerNorm latency is hidden behind the ring.
+// out_proj is applied twice by the reference (_torch.py:419-420): its slice is held in the ring between the two
+// passes, so it is read from HBM once.
+// ================================================================================================================
+struct MegaLayer { const bf16 *norm_w, *norm_b, *in_proj, *out_proj, *norm2_w, *norm2_b, *fc1, *fc2; bf16* kv_layer; };
+
+struct MegaArgs {
+  const MegaLayer* layers; int n_layer;
+  int D, F, Hq, Hkv, hd; float eps; int norm_kind, rope_interleaved, out_proj_repeats;
+  const bf16 *normf_w, *normf_b, *heads; int QV, B; float cfg_scale; float* logits;
+  const float* rope; int rope_len;
+  const int32_t* lengths; const int32_t* page_table; int max_pages;
+  const bf16* emb[16]; int Q, vocab; const int64_t* delayed; int T_delayed;
+  bf16 *x, *q, *attn_y, *y1, *h; float* attn_part; int32_t* attn_counters; int nsplit; float scale;
+  const zb_loop_state* loop;
+  unsigned* bar;          // [0] arrivals, [1] generation
+  int ring_stages, part_bytes;
+  unsigned long long* timeline;   // debug: globaltimer stamps of CTA 0 (2 per phase: work done, barrier passed)
+};
+
+constexpr int kMegaStageBytes = 32 * 1024;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// grid-wide barrier among the consumer warps of all CTAs: monotonic arrival counter (reset to 0 between steps by
+// the sampler kernel that follows every step), arrive = red.release (fire and forget), wait = ld.acquire spin.
+__device__ __forceinline__ void mega_grid_barrier(unsigned* bar, unsigned& target) {
+  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    for (unsigned spins = 0; ld_acquire_u32(bar) < target; ++spins)
+      if (spins > (1u << 26)) asm volatile("trap;");         // a lost CTA must end in an error, not a hung GPU
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+}
+
+template <int EPI>
+__device__ __forceinline__ void mega_slice(const GemvArgs& a, int& u_begin, int& nrows) {
+  constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
+  const int nunits = units_total<EPI>(a);
+  u_begin = (int)((long long)blockIdx.x * nunits / gridDim.x);
+  const int u_end = (int)((long long)(blockIdx.x + 1) * nunits / gridDim.x);
+  nrows = (u_end - u_begin) * (kPairs ? 2 : 1);
+}
+
+// producer: stream this CTA's slice of one matrix through the ring (global stage counter gst)
+template <int EPI>
+__device__ __forceinline__ void mega_produce(const GemvArgs& a, unsigned char* ring, uint64_t* full_bar, uint64_t* empty_bar, int S, int& gst,
+                                             uint64_t pol, int lane) {
+  constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
+  const int K = a.K, row_bytes = K * 2, RPS = kMegaStageBytes / row_bytes;
+  int u_begin, nrows;
+  mega_slice<EPI>(a, u_begin, nrows);
+  const int nstage = (nrows + RPS - 1) / RPS;
+  for (int st = 0; st < nstage; ++st, ++gst) {
+    const int slot = gst % S;
+    if (gst >= S) mbar_wait(&empty_bar[slot], ((gst / S) - 1) & 1);
+    const int r0 = st * RPS;
+    if (lane == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)kMegaStageBytes);
+    __syncwarp();
+    unsigned char* dst = ring + (size_t)slot * kMegaStageBytes;
+    if (!kPairs && r0 + RPS <= nrows) {
+      if (lane == 0) bulk_g2s(dst, a.W + (size_t)(u_begin + r0) * K, (uint32_t)kMegaStageBytes, &full_bar[slot], pol);
+    } else {
+      for (int q = lane; q < RPS; q += 32) {
+        const int lr = min(r0 + q, nrows - 1);
+        bulk_g2s(dst + (size_t)q * row_bytes, a.W + (size_t)row_of_local<EPI>(a, u_begin, lr) * K, row_bytes, &full_bar[slot], pol);
+      }
+    }
+  }
+}
+
+// consumers: one matrix phase.  wait_full / release control the out_proj "hold" (first pass keeps the slots).
+template <int R, int NC, int RW, int PRO, int EPI>
+__device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* ring, float* part, uint64_t* full_bar, uint64_t* empty_bar,
+                                             float (*red)[kW3][4], int S, int& gst, bool release, int warp, int lane) {
+  constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
+  constexpr int Kc = NC * 256;
+  const int K = a.K, row_bytes = K * 2;
+  const int KS = K / Kc;
+  const int RPS = (kW3 / KS) * RW;
+  int u_begin, nrows;
+  mega_slice<EPI>(a, u_begin, nrows);
+  const int nstage = (nrows + RPS - 1) / RPS;
+  const int ks = warp % KS, rg = warp / KS;
+  const size_t koff = (size_t)ks * Kc;
+  uint4 nwr[NC], nbr[NC];                                      // norm parameters: in flight together with the activations
+  if (PRO == PRO_NORM) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const size_t k = koff + c * 256 + lane * 8;
+      nwr[c] = *reinterpret_cast<const uint4*>(a.nw + k);
+      nbr[c] = a.nb ? *reinterpret_cast<const uint4*>(a.nb + k) : make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  float xf[R][NC * 8];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const uint4 v = (i < a.M) ? __ldcg(reinterpret_cast<const uint4*>(a.x + (size_t)i * a.ldx + koff + c * 256 + lane * 8)) : make_uint4(0, 0, 0, 0);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xf[i][c * 8 + 2 * j] = bf16lo(w4[j]); xf[i][c * 8 + 2 * j + 1] = bf16hi(w4[j]); }
+    }
+  if (PRO == PRO_NORM) {
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float sacc = 0.f, qacc = 0.f;
+#pragma unroll
+      for (int e = 0; e < NC * 8; ++e) { sacc += xf[i][e]; qacc = fmaf(xf[i][e], xf[i][e], qacc); }
+      sacc = warp_sum(sacc);
+      qacc = warp_sum(qacc);
+      if (rg == 0 && lane == 0) { red[0][ks][i] = sacc; red[1][ks][i] = qacc; }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float tot = 0.f, tsq = 0.f;
+      for (int q = 0; q < KS; ++q) { tot += red[0][q][i]; tsq += red[1][q][i]; }
+      const float mu = tot / (float)K;
+      mean[i] = (a.norm_kind == ZB_NORM_LAYERNORM) ? mu : 0.f;
+      const float var = (a.norm_kind == ZB_NORM_LAYERNORM) ? fmaxf(tsq / (float)K - mu * mu, 0.f) : tsq / (float)K;
+      rstd[i] = rsqrtf(var + a.eps);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const uint32_t gv[4] = {nwr[c].x, nwr[c].y, nwr[c].z, nwr[c].w}, bv[4] = {nbr[c].x, nbr[c].y, nbr[c].z, nbr[c].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g0 = bf16lo(gv[j]), g1 = bf16hi(gv[j]), b0 = bf16lo(bv[j]), b1 = bf16hi(bv[j]);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          xf[i][c * 8 + 2 * j] = rbf((xf[i][c * 8 + 2 * j] - mean[i]) * rstd[i] * g0 + b0);
+          xf[i][c * 8 + 2 * j + 1] = rbf((xf[i][c * 8 + 2 * j + 1] - mean[i]) * rstd[i] * g1 + b1);
+        }
+      }
+    }
+  }
+  unsigned long long x2[R][NC * 4];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int e = 0; e < NC * 4; ++e) x2[i][e] = pack_f32x2(xf[i][2 * e], xf[i][2 * e + 1]);
+
+  constexpr int V = RW * R;
+  const int my_idx = multi_reduce_index<V>(lane);
+  const bool writer = (lane & ((32 / V) - 1)) == 0;
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t lane_base = smem_u32(ring) + (uint32_t)(rg * RW) * row_bytes + (uint32_t)(koff + lane * 8) * 2;
+  const uint32_t part_lane = smem_u32(part) + (uint32_t)((((rg * RW + my_idx / R) * KS + ks) * R + my_idx % R) * 4);
+  const uint32_t part_stage = (uint32_t)(RPS * KS * R * 4);
+  for (int st = 0; st < nstage; ++st, ++gst) {
+    const uint32_t slot = (uint32_t)(gst % S), phase = (uint32_t)((gst / S) & 1);
+    mbar_wait_u32(full0 + slot * 8, phase);
+    const uint32_t src = lane_base + slot * kMegaStageBytes;
+    unsigned long long acc2[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc2[q] = 0ull;
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const uint4 wv = lds128(src + w * row_bytes + c * 512);
+        const uint32_t c0[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const unsigned long long w2 = pack_f32x2(bf16lo(c0[jj]), bf16hi(c0[jj]));
+#pragma unroll
+          for (int i = 0; i < R; ++i) ffma2(acc2[w * R + i], w2, x2[i][c * 4 + jj]);
+        }
+      }
+    }
+    __syncwarp();
+    if (release && lane == 0) mbar_arrive_u32(empty0 + slot * 8);
+    float acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = sum_f32x2(acc2[q]);
+    warp_reduce_multi<V>(acc);
+    if (writer) sts32(part_lane + st * part_stage, acc[0]);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+
+  const bool cfg = (EPI == EPI_HEADS && a.cfg_scale != 1.0f);
+  const int rows_out = cfg ? a.B : a.M;
+  const int nu = kPairs ? nrows / 2 : nrows;
+  for (int t = threadIdx.x; t < nu * rows_out; t += kW3 * 32) {
+    const int j = t / rows_out, i = t % rows_out;
+    int n0, n1;
+    float v0 = 0.f, v1 = 0.f, u0 = 0.f, u1 = 0.f;
+    if (kPairs) {
+      unit_rows<EPI>(a, u_begin + j, n0, n1);
+      const float* s0 = part + (size_t)(2 * j) * KS * R;
+      const float* s1 = s0 + (size_t)KS * R;
+      for (int q = 0; q < KS; ++q) { v0 += s0[q * R + i]; v1 += s1[q * R + i]; }
+      gemv_epilogue<EPI>(a, i, n0, n1, true, v0, v1, 0.f, 0.f);
+    } else {
+      n0 = u_begin + j; n1 = n0 + 1;
+      const float* s0 = part + (size_t)j * KS * R;
+      for (int q = 0; q < KS; ++q) { v0 += s0[q * R + i]; if (cfg) u0 += s0[q * R + a.B + i]; }
+      gemv_epilogue<EPI>(a, i, n0, n1, false, v0, v1, u0, u1);
+    }
+  }
+}
+
+// attention for one (row, kv head, split) unit by the consumer warps (warps 0..G-1 compute, all 16 load and sync)
+// K/V of the tokens cached by EARLIER steps for this CTA's first attention unit of the layer: issued before the
+// in_proj phase so the tile is already in shared memory when the attention phase starts
+__device__ __forceinline__ void mega_attention_prefetch(const MegaArgs& m, const bf16* kv_layer, int unit, int nunits, unsigned char* scratch) {
+  if (unit >= nunits) return;
+  bf16* ks = reinterpret_cast<bf16*>(scratch);
+  bf16* vs = ks + kCH * kKStride;
+  const int split = unit % m.nsplit, g = (unit / m.nsplit) % m.Hkv, r = unit / (m.nsplit * m.Hkv);
+  const int kv_len = m.lengths[r] + 1;
+  const int k0 = split * kCH;
+  const int n_old = min(kCH, kv_len - 1 - k0);
+  if (n_old <= 0) return;
+  const int page = m.page_table[(size_t)r * m.max_pages + split];
+  const bf16* kp = kv_layer + (((size_t)page * 2 + 0) * m.Hkv + g) * kCH * kHD;
+  const bf16* vp = kv_layer + (((size_t)page * 2 + 1) * m.Hkv + g) * kCH * kHD;
+  for (int c = threadIdx.x; c < kCH * kHD / 8; c += kW3 * 32) {
+    const int tok = c / (kHD / 8), d8 = (c % (kHD / 8)) * 8;
+    if (tok < n_old) {
+      cp_async16(ks + tok * kKStride + d8, kp + tok * kHD + d8);
+      cp_async16(vs + tok * kHD + d8, vp + tok * kHD + d8);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf16* kv_layer, int unit, unsigned char* scratch, int warp, int lane,
+                                                    bool prefetched) {
+  bf16* ks = reinterpret_cast<bf16*>(scratch);                         // [64][136]
+  bf16* vs = ks + kCH * kKStride;                                      // [64][128]
+  float* qs = reinterpret_cast<float*>(vs + kCH * kHD);                // [8][128]
+  float* ps = qs + 8 * kHD;                                            // [8][64]
+  int* s_last = reinterpret_cast<int*>(ps + 8 * kCH);
+  const int G = m.Hq / m.Hkv;
+  const int split = unit % m.nsplit, g = (unit / m.nsplit) % m.Hkv, r = unit / (m.nsplit * m.Hkv);
+  const int kv_len = m.lengths[r] + 1;
+  const int nact = (kv_len + kCH - 1) / kCH;
+  if (split >= nact) return;                                            // uniform for the CTA
+  const int k0 = split * kCH, nk = min(kCH, kv_len - k0);
+  const int page = m.page_table[(size_t)r * m.max_pages + split];
+  const bf16* kp = kv_layer + (((size_t)page * 2 + 0) * m.Hkv + g) * kCH * kHD;
+  const bf16* vp = kv_layer + (((size_t)page * 2 + 1) * m.Hkv + g) * kCH * kHD;
+  // tokens cached by earlier steps were prefetched (mega_attention_prefetch, before the in_proj phase) when
+  // `prefetched`; this step's own token (index kv_len-1) is fetched now
+  const int n_old = prefetched ? max(0, min(nk, kv_len - 1 - k0)) : 0;
+  for (int c = threadIdx.x; c < kCH * kHD / 8; c += kW3 * 32) {
+    const int tok = c / (kHD / 8), d8 = (c % (kHD / 8)) * 8;
+    if (tok >= n_old && tok < nk) {
+      cp_async16(ks + tok * kKStride + d8, kp + tok * kHD + d8);
+      cp_async16(vs + tok * kHD + d8, vp + tok * kHD + d8);
+    } else if (tok >= nk) {
+      *reinterpret_cast<uint4*>(ks + tok * kKStride + d8) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(vs + tok * kHD + d8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  const int head = g * G + warp;
+  if (warp < G) {
+    const uint2 qv = __ldcg(reinterpret_cast<const uint2*>(m.q + (size_t)r * m.Hq * kHD + (size_t)head * kHD + lane * 4));
+    qs[warp * kHD + lane * 4 + 0] = bf16lo(qv.x); qs[warp * kHD + lane * 4 + 1] = bf16hi(qv.x);
+    qs[warp * kHD + lane * 4 + 2] = bf16lo(qv.y); qs[warp * kHD + lane * 4 + 3] = bf16hi(qv.y);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  if (warp < G) {
+    float sc[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tok = lane + 32 * j;
+      float sacc = 0.f;
+#pragma unroll
+      for (int d8 = 0; d8 < kHD; d8 += 8) {
+        const uint4 kv4 = *reinterpret_cast<const uint4*>(ks + tok * kKStride + d8);
+        const float4 q0 = *reinterpret_cast<const float4*>(&qs[warp * kHD + d8]);
+        const float4 q1 = *reinterpret_cast<const float4*>(&qs[warp * kHD + d8 + 4]);
+        sacc = fmaf(bf16lo(kv4.x), q0.x, sacc); sacc = fmaf(bf16hi(kv4.x), q0.y, sacc);
+        sacc = fmaf(bf16lo(kv4.y), q0.z, sacc); sacc = fmaf(bf16hi(kv4.y), q0.w, sacc);
+        sacc = fmaf(bf16lo(kv4.z), q1.x, sacc); sacc = fmaf(bf16hi(kv4.z), q1.y, sacc);
+        sacc = fmaf(bf16lo(kv4.w), q1.z, sacc); sacc = fmaf(bf16hi(kv4.w), q1.w, sacc);
+      }
+      sc[j] = (tok < nk) ? sacc * m.scale : -INFINITY;
+    }
+    const float mx = warp_max(fmaxf(sc[0], sc[1]));
+    const float p0 = __expf(sc[0] - mx), p1 = __expf(sc[1] - mx);
+    const float l = warp_sum(p0 + p1);
+    ps[warp * kCH + lane] = p0; ps[warp * kCH + lane + 32] = p1;
+    __syncwarp();
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tok = 0; tok < nk; ++tok) {
+      const float pp = ps[warp * kCH + tok];
+      const uint2 vv = *reinterpret_cast<const uint2*>(vs + tok * kHD + lane * 4);
+      o[0] = fmaf(pp, bf16lo(vv.x), o[0]); o[1] = fmaf(pp, bf16hi(vv.x), o[1]);
+      o[2] = fmaf(pp, bf16lo(vv.y), o[2]); o[3] = fmaf(pp, bf16hi(vv.y), o[3]);
+    }
+    float* part = m.attn_part + (((size_t)r * m.Hq + head) * m.nsplit + split) * kPart;
+    *reinterpret_cast<float4*>(part + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    if (lane == 0) { part[kHD] = mx; part[kHD + 1] = l; }
+    __threadfence();
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  if (threadIdx.x == 0) {
+    int32_t* cnt = m.attn_counters + (size_t)r * m.Hkv + g;
+    const int prev = atomicAdd(cnt, 1);
+    *s_last = (prev == nact - 1);
+    if (*s_last) *cnt = 0;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  if (*s_last && warp < G) {
+    __threadfence();
+    const float* base = m.attn_part + (((size_t)r * m.Hq + head) * m.nsplit) * kPart;
+    float M = -INFINITY;
+    for (int sp = 0; sp < nact; ++sp) M = fmaxf(M, __ldcg(base + (size_t)sp * kPart + kHD));
+    float L = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int sp = 0; sp < nact; ++sp) {
+      const float* ps_ = base + (size_t)sp * kPart;
+      const float w = __expf(__ldcg(ps_ + kHD) - M);
+      L = fmaf(__ldcg(ps_ + kHD + 1), w, L);
+      const float4 ov = __ldcg(reinterpret_cast<const float4*>(ps_ + lane * 4));
+      acc[0] = fmaf(ov.x, w, acc[0]); acc[1] = fmaf(ov.y, w, acc[1]);
+      acc[2] = fmaf(ov.z, w, acc[2]); acc[3] = fmaf(ov.w, w, acc[3]);
+    }
+    const float inv = 1.0f / L;
+    uint2 outv;
+    outv.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+    outv.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+    *reinterpret_cast<uint2*>(m.attn_y + (size_t)r * m.Hq * kHD + (size_t)head * kHD + lane * 4) = outv;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");       // scratch free for the next unit
+}
+
+__device__ __forceinline__ void mega_fill(GemvArgs& a, const MegaArgs& m, int R) {
+  memset(&a, 0, sizeof(a));
+  a.M = R; a.eps = m.eps; a.norm_kind = m.norm_kind; a.T = 1; a.Hq = m.Hq; a.Hkv = m.Hkv; a.hd = m.hd;
+  a.rope_interleaved = m.rope_interleaved; a.rope = m.rope; a.rope_len = m.rope_len; a.lengths = m.lengths;
+  a.page_table = m.page_table; a.max_pages = m.max_pages; a.F = m.F; a.B = m.B; a.cfg_scale = m.cfg_scale; a.logits = m.logits; a.QV = m.QV;
+}
+
+template <int R>
+__global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __grid_constant__ MegaArgs m) {
+  extern __shared__ __align__(128) unsigned char smem_m[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ float red[2][kW3][4];
+  if (loop_idle(m.loop, m.T_delayed)) return;                 // same answer in every CTA: the loop state only changes in the sampler
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = m.ring_stages;
+  unsigned char* ring = smem_m;
+  float* part = reinterpret_cast<float*>(smem_m + (size_t)S * kMegaStageBytes);
+  unsigned char* attn_scratch = smem_m + (size_t)S * kMegaStageBytes + m.part_bytes;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kW3); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int qn = m.Hq * m.hd, nqkv = (m.Hq + 2 * m.Hkv) * m.hd;
+  GemvArgs a;
+
+  if (warp == kW3) {
+    // ===== producer: the whole step's weights, in consumption order =====
+    const uint64_t pol = l2_evict_first_policy();
+    int gst = 0;
+    for (int li = 0; li < m.n_layer; ++li) {
+      const MegaLayer& L = m.layers[li];
+      mega_fill(a, m, R);
+      a.W = L.in_proj; a.N = nqkv; a.K = m.D;
+      mega_produce<EPI_QKV>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+      a.W = L.out_proj; a.N = m.D; a.K = qn;
+      mega_produce<EPI_STORE>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+      a.W = L.fc1; a.N = 2 * m.F; a.K = m.D;
+      mega_produce<EPI_SILU>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+      a.W = L.fc2; a.N = m.D; a.K = m.F;
+      mega_produce<EPI_RESID>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+    }
+    mega_fill(a, m, R);
+    a.W = m.heads; a.N = m.QV; a.K = m.D;
+    mega_produce<EPI_HEADS>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+    return;
+  }
+
+  // ===== consumers =====
+  unsigned gen = 0;                                         // arrivals expected so far (the counter starts every step at 0)
+  int gst = 0;
+  int stamp_i = 0;
+#define MEGA_STAMP() do { if (m.timeline && blockIdx.x == 0 && threadIdx.x == 0 && stamp_i < 126) m.timeline[stamp_i] = gtime(); ++stamp_i; } while (0)
+  MEGA_STAMP();
+  // phase 0: codebook embedding sum (sequential bf16 adds, codec_utils.py:37) for this CTA's columns, both CFG rows
+  {
+    const int d_begin = (int)((long long)blockIdx.x * m.D / gridDim.x), d_end = (int)((long long)(blockIdx.x + 1) * m.D / gridDim.x);
+    const long long col = m.loop ? (long long)m.loop->offset : 0;
+    for (int t = threadIdx.x; t < (d_end - d_begin) * m.B; t += kW3 * 32) {
+      const int b = t / (d_end - d_begin), dd = d_begin + t % (d_end - d_begin);
+      float acc = 0.f;
+      for (int k = 0; k < m.Q; ++k) {
+        long long id = m.delayed[((size_t)b * m.Q + k) * m.T_delayed + col];
+        id = id < 0 ? 0 : (id >= m.vocab ? m.vocab - 1 : id);
+        acc = rbf(acc + bf2f(m.emb[k][(size_t)id * m.D + dd]));
+      }
+      m.x[(size_t)b * m.D + dd] = f2bf(acc);
+      m.x[(size_t)(m.B + b) * m.D + dd] = f2bf(acc);
+    }
+  }
+  MEGA_STAMP(); mega_grid_barrier(m.bar, gen); MEGA_STAMP();
+
+  for (int li = 0; li < m.n_layer; ++li) {
+    const MegaLayer& L = m.layers[li];
+    // A: norm -> in_proj -> RoPE -> KV append (+ q)
+    mega_fill(a, m, R);
+    a.W = L.in_proj; a.N = nqkv; a.K = m.D; a.x = m.x; a.ldx = m.D; a.nw = L.norm_w; a.nb = L.norm_b; a.kv_layer = L.kv_layer; a.q_out = m.q;
+    mega_attention_prefetch(m, L.kv_layer, blockIdx.x, R * m.Hkv * m.nsplit, attn_scratch);
+    mega_consume<R, 1, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane);
+    MEGA_STAMP(); mega_grid_barrier(m.bar, gen); MEGA_STAMP();
+    // B: attention over the paged cache
+    for (int unit = blockIdx.x; unit < R * m.Hkv * m.nsplit; unit += gridDim.x)
+      mega_attention_unit(m, L.kv_layer, unit, attn_scratch, warp, lane, unit == (int)blockIdx.x);
+    MEGA_STAMP(); mega_grid_barrier(m.bar, gen); MEGA_STAMP();
+    // C/D: out_proj (twice in the reference); the slice stays in the ring between the passes
+    {
+      const int gst0 = gst;
+      const bf16* src = m.attn_y;
+      for (int rep = 0; rep < m.out_proj_repeats; ++rep) {
+        const bool last = rep == m.out_proj_repeats - 1;
+        mega_fill(a, m, R);
+        a.W = L.out_proj; a.N = m.D; a.K = qn; a.x = src; a.ldx = qn;
+        int g2 = gst0;
+        if (last) {
+          a.y = m.x; a.ldy = m.D; a.resid = m.x; a.ldr = m.D;
+          mega_consume<R, 1, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane);
+        } else {
+          bf16* dst = (src == m.y1) ? m.attn_y : m.y1;
+          a.y = dst; a.ldy = m.D;
+          mega_consume<R, 1, 4, PRO_NONE, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, g2, false, warp, lane);
+          src = dst;
+        }
+        gst = g2;
+        MEGA_STAMP(); mega_grid_barrier(m.bar, gen); MEGA_STAMP();
+      }
+    }
+    // E: norm2 -> fc1 -> value * silu(gate)
+    mega_fill(a, m, R);
+    a.W = L.fc1; a.N = 2 * m.F; a.K = m.D; a.x = m.x; a.ldx = m.D; a.nw = L.norm2_w; a.nb = L.norm2_b; a.y = m.h; a.ldy = m.F;
+    mega_consume<R, 1, 4, PRO_NORM, EPI_SILU>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane);
+    MEGA_STAMP(); mega_grid_barrier(m.bar, gen); MEGA_STAMP();
+    // F: fc2 + residual
+    mega_fill(a, m, R);
+    a.W = L.fc2; a.N = m.D; a.K = m.F; a.x = m.h; a.ldx = m.F; a.y = m.x; a.ldy = m.D; a.resid = m.x; a.ldr = m.D;
+    if (m.F == 8192) mega_consume<R, 2, 2, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane);
+    else mega_consume<R, 1, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane);
+    MEGA_STAMP(); mega_grid_barrier(m.bar, gen); MEGA_STAMP();
+  }
+  // heads: final norm -> fused heads -> fp32 -> CFG mix
+  mega_fill(a, m, R);
+  a.W = m.heads; a.N = m.QV; a.K = m.D; a.x = m.x; a.ldx = m.D; a.nw = m.normf_w; a.nb = m.normf_b;
+  mega_consume<R, 1, 4, PRO_NORM, EPI_HEADS>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane);
+  MEGA_STAMP();
+#undef MEGA_STAMP
+}
+
 // ------------------------------------------------------------------ plain norm ---------------
 struct NormArgs { const bf16* x; int64_t ldx; bf16* y; int64_t ldy; const bf16* w; const bf16* b; int D; float eps; int kind; };
 __global__ void __launch_bounds__(256) norm_kernel(NormArgs a) {
@@ -996,8 +1473,101 @@ zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden
   return launch_gemv<PRO_NONE, EPI_HEADS>(ctx, a, stream);
 }
 
-// ---- diagnostics: launch ONE production kernel on scratch activations (bench.py roofline leg) ----
+
 static unsigned long long* g_timeline = nullptr;   // debug: set by zb_debug_timeline
+
+// ---- persistent decode step (host side) ----
+size_t zb_mega_layers_bytes(const zb_model* model) { return (size_t)model->d.n_layer * sizeof(MegaLayer); }
+
+zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf) {
+  const zb_model_desc& d = model->d;
+  const size_t page_elems = (size_t)2 * d.n_heads_kv * ZB_PAGE_TOKENS * d.head_dim;
+  MegaLayer* out = (MegaLayer*)host_buf;
+  for (int li = 0; li < d.n_layer; ++li) {
+    const zb_layer& L = model->layers[li];
+    ZB_REQUIRE(ctx, L.kind == ZB_LAYER_ATTENTION, "persistent decode: layer %d is not an attention layer", li);
+    out[li].norm_w = (const bf16*)L.norm_w; out[li].norm_b = (const bf16*)L.norm_b; out[li].in_proj = (const bf16*)L.in_proj;
+    out[li].out_proj = (const bf16*)L.out_proj; out[li].norm2_w = (const bf16*)L.norm2_w; out[li].norm2_b = (const bf16*)L.norm2_b;
+    out[li].fc1 = (const bf16*)L.fc1; out[li].fc2 = (const bf16*)L.fc2;
+    out[li].kv_layer = (bf16*)cache->kv_pages + (size_t)model->attn_index[li] * cache->num_pages * page_elems;
+  }
+  return ZB_OK;
+}
+
+bool zb_mega_supported(const zb_model* model, int R) {
+  const zb_model_desc& d = model->d;
+  static const int enabled = env_int("ZB_DECODE_MEGA", 1);
+  auto k_ok = [](int K) { return K == 256 || K == 512 || K == 1024 || K == 2048 || K == 4096; };
+  const int qn = d.n_heads * d.head_dim;
+  return enabled && R >= 2 && R <= 4 && d.head_dim == kHD && k_ok(d.d_model) && k_ok(qn) && (k_ok(d.d_ff) || d.d_ff == 8192) &&
+         d.n_codebooks <= 16 && d.n_heads / d.n_heads_kv <= 8 && (d.out_proj_repeats == 1 || qn == d.d_model) &&
+         d.out_proj_repeats >= 1 && d.out_proj_repeats <= 2 && (((d.n_heads + 2 * d.n_heads_kv) * d.head_dim) % 2 == 0);
+}
+
+zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const void* mega_layers_dev, unsigned* bar,
+                                bf16* x, int R, int max_kv_len, float cfg_scale, float* logits, const int64_t* delayed, int T_delayed,
+                                const zb_loop_state* loop, cudaStream_t stream) {
+  const zb_model_desc& d = model->d;
+  const int nsplit = (max_kv_len + kCH - 1) / kCH;
+  size_t need = 0;
+  carve(model, nullptr, R, nsplit, &need);
+  ZB_REQUIRE(ctx, ctx->scratch_bytes >= need, "internal: scratch not reserved (%zu < %zu)", ctx->scratch_bytes, need);
+  Scratch s = carve(model, ctx->scratch, R, nsplit, nullptr);
+  MegaArgs m;
+  memset(&m, 0, sizeof(m));
+  m.layers = (const MegaLayer*)mega_layers_dev; m.n_layer = d.n_layer;
+  m.D = d.d_model; m.F = d.d_ff; m.Hq = d.n_heads; m.Hkv = d.n_heads_kv; m.hd = d.head_dim; m.eps = d.norm_eps; m.norm_kind = d.norm_kind;
+  m.rope_interleaved = d.rope_interleaved; m.out_proj_repeats = d.out_proj_repeats;
+  m.normf_w = (const bf16*)d.norm_f_w; m.normf_b = (const bf16*)d.norm_f_b; m.heads = (const bf16*)d.heads; m.QV = d.n_codebooks * d.head_vocab;
+  m.B = R / 2; m.cfg_scale = cfg_scale; m.logits = logits; m.rope = d.rope_table; m.rope_len = d.rope_len;
+  m.lengths = cache->lengths; m.page_table = cache->page_table; m.max_pages = cache->max_pages_per_row;
+  for (int k = 0; k < d.n_codebooks; ++k) m.emb[k] = (const bf16*)model->emb[k];
+  m.Q = d.n_codebooks; m.vocab = d.emb_vocab; m.delayed = delayed; m.T_delayed = T_delayed;
+  m.x = x; m.q = s.q; m.attn_y = s.attn_y; m.y1 = s.y1; m.h = s.h; m.attn_part = s.part; m.attn_counters = ctx->counters; m.nsplit = nsplit;
+  m.scale = 1.0f / sqrtf((float)d.head_dim); m.loop = loop; m.bar = bar; m.timeline = g_timeline;
+  ZB_REQUIRE(ctx, cfg_scale != 1.0f, "persistent decode expects CFG rows");
+  const int grid = ctx->num_sms;
+  // partial-sum buffer: the largest padded row count x k-slices over all matrices of the step
+  auto part_need = [&](int nunits, bool pairs, int K, int NC, int RW) {
+    const int KS = K / (NC * 256), RPS = (kW3 / KS) * RW;
+    const int rows = ((nunits + grid - 1) / grid) * (pairs ? 2 : 1);
+    return (size_t)((rows + RPS - 1) / RPS * RPS) * KS * R * sizeof(float);
+  };
+  const int qn = d.n_heads * d.head_dim;
+  size_t pb = part_need((d.n_heads + 2 * d.n_heads_kv) * d.head_dim / 2, true, d.d_model, 1, 4);
+  pb = std::max(pb, part_need(d.d_model, false, qn, 1, 4));
+  pb = std::max(pb, part_need(d.d_ff, true, d.d_model, 1, 4));
+  pb = std::max(pb, d.d_ff == 8192 ? part_need(d.d_model, false, d.d_ff, 2, 2) : part_need(d.d_model, false, d.d_ff, 1, 4));
+  pb = std::max(pb, part_need(m.QV, false, d.d_model, 1, 4));
+  pb = (pb + 1023) / 1024 * 1024;
+  const size_t attn_bytes = 40 * 1024;
+  const size_t avail = 227 * 1024 - 2048;
+  int stages = (int)((avail - pb - attn_bytes) / kMegaStageBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  ZB_REQUIRE(ctx, stages >= 3, "persistent decode: not enough shared memory for the ring");
+  m.ring_stages = stages; m.part_bytes = (int)pb;
+  const size_t smem = (size_t)stages * kMegaStageBytes + pb + attn_bytes;
+  auto launch = [&](auto kernel) -> zb_status {
+    static size_t attr = 0;
+    if (smem > attr) {
+      ZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((kW3 + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;      // all CTAs must be co-resident: the phases meet at grid barriers
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, m));
+    ctx->launches++;
+    return ZB_OK;
+  };
+  if (R <= 2) return launch(decode_step_kernel<2>);
+  return launch(decode_step_kernel<4>);
+}
+
+// ---- diagnostics: launch ONE production kernel on scratch activations (bench.py roofline leg) ----
 extern "C" ZB_API zb_status zb_debug_timeline(unsigned long long* dev_buf) { g_timeline = dev_buf; return ZB_OK; }
 
 extern "C" zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows, int32_t iters,

@@ -36,6 +36,7 @@ struct zb_sample_launch {
   int32_t* lengths = nullptr; const float* q_stream = nullptr; int q_calls = 0;
   float* logits_trace = nullptr; int trace_calls = 0; int first = 0; int prefix_len = 0;
   int32_t* mirror = nullptr;   // host-mapped copy of the first 8 words of zb_loop_state (device pointer)
+  unsigned* reset_word = nullptr;   // zeroed by the kernel (grid-barrier counter of the persistent decode step)
 };
 zb_status zb_launch_sample(zb_ctx* ctx, const zb_sample_launch& L, cudaStream_t stream);
 
@@ -60,6 +61,13 @@ zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden
                           int apply_norm, float cfg_scale, float* logits, const zb_loop_state* loop, int T_delayed,
                           cudaStream_t stream);
 size_t zb_backbone_scratch_bytes(const zb_model* model, int R, int T, int max_kv_len);
+// persistent single-launch decode step (decode.cu)
+bool zb_mega_supported(const zb_model* model, int R);
+size_t zb_mega_layers_bytes(const zb_model* model);
+zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf);
+zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const void* mega_layers_dev, unsigned* bar,
+                                bf16* x, int R, int max_kv_len, float cfg_scale, float* logits, const int64_t* delayed, int T_delayed,
+                                const zb_loop_state* loop, cudaStream_t stream);
 
 // ---- tcgen05 GEMM (gemm_tc.cu): Y[M,N] = X[M,K] W[N,K]^T with fused epilogue ----
 struct zb_gemm_tc {

@@ -67,6 +67,7 @@ struct SampleArgs {
   int first;                  // 1: the post-prefill sample (model.py:423-431)
   int prefix_len;             // Lc + P + 1 (first only)
   int32_t* mirror;            // host-mapped progress words (offset, step_idx, done, steps)
+  unsigned* reset_word;       // grid-barrier counter of the persistent decode kernel: zeroed after every step
 };
 
 __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
   zb_loop_state* st = a.st;
   pdl_launch_dependents();
   pdl_wait();
+  if (a.reset_word && blockIdx.x == 0 && threadIdx.x == 0) *a.reset_word = 0;
 
   int offset_new = 0;
   uint64_t draw = a.draw_index;
@@ -426,7 +428,7 @@ zb_status zb_launch_sample(zb_ctx* ctx, const zb_sample_launch& L, cudaStream_t 
   a.q = L.q; a.seed = L.seed; a.draw_index = L.draw_index; a.sp = L.sp; a.apply_bias = L.apply_bias;
   a.tokens = L.tokens; a.st = L.st; a.delayed = L.delayed; a.T = L.T; a.ctx_len = L.ctx_len;
   a.lengths = L.lengths; a.q_stream = L.q_stream; a.q_calls = L.q_calls; a.logits_trace = L.logits_trace;
-  a.trace_calls = L.trace_calls; a.first = L.first; a.prefix_len = L.prefix_len; a.mirror = L.mirror;
+  a.trace_calls = L.trace_calls; a.first = L.first; a.prefix_len = L.prefix_len; a.mirror = L.mirror; a.reset_word = L.reset_word;
   ZB_REQUIRE(ctx, L.Q >= 1 && L.Q <= 16, "sampler: Q=%d unsupported (1..16)", L.Q);
   ZB_REQUIRE(ctx, L.V >= 2 && L.V <= SAMP_MAXV, "sampler: V=%d unsupported (<= %d)", L.V, SAMP_MAXV);
   ZB_REQUIRE(ctx, L.B >= 1, "sampler: B=%d", L.B);

@@ -851,6 +851,32 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
 #pragma unroll
     for (int e = 0; e < NC * 4; ++e) x2[i][e] = pack_f32x2(xf[i][2 * e], xf[i][2 * e + 1]);
 
+  // ---- operands of this thread's epilogue (residual value, RoPE cos/sin, KV page): fetched NOW so their L2 round
+  // trips overlap the weight streaming instead of trailing it ----
+  const bool cfg = (EPI == EPI_HEADS && a.cfg_scale != 1.0f);
+  const int rows_out = cfg ? a.B : a.M;
+  const int nu = kPairs ? nrows / 2 : nrows;
+  const int et = threadIdx.x;                                 // one epilogue item per thread (host guarantees nu*rows_out <= 512)
+  const bool e_on = et < nu * rows_out;
+  const int ej = e_on ? et / rows_out : 0, ei = e_on ? et % rows_out : 0;
+  int en0 = 0, en1 = 1;
+  if (kPairs) unit_rows<EPI>(a, u_begin + ej, en0, en1); else { en0 = u_begin + ej; en1 = en0 + 1; }
+  float pre_resid = 0.f;
+  float2 pre_cs = make_float2(1.f, 0.f);
+  int pre_pos = 0, pre_page = 0;
+  if (e_on) {
+    if (EPI == EPI_RESID) pre_resid = ldcg_bf16(a.resid + (size_t)ei * a.ldr + en0);
+    if (EPI == EPI_QKV) {
+      pre_pos = a.lengths[ei];
+      const int qn_ = a.Hq * a.hd, kn_ = a.Hkv * a.hd;
+      if (en0 < qn_ + kn_) {
+        const int ri = a.rope_interleaved ? (en0 % a.hd) / 2 : (en0 % a.hd);
+        pre_cs = *reinterpret_cast<const float2*>(a.rope + ((size_t)min(pre_pos, a.rope_len - 1) * (a.hd / 2) + ri) * 2);
+      }
+      if (en0 >= qn_) pre_page = a.page_table[(size_t)ei * a.max_pages + pre_pos / ZB_PAGE_TOKENS];
+    }
+  }
+
   constexpr int V = RW * R;
   const int my_idx = multi_reduce_index<V>(lane);
   const bool writer = (lane & ((32 / V) - 1)) == 0;
@@ -889,46 +915,65 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
 
-  const bool cfg = (EPI == EPI_HEADS && a.cfg_scale != 1.0f);
-  const int rows_out = cfg ? a.B : a.M;
-  const int nu = kPairs ? nrows / 2 : nrows;
-  for (int t = threadIdx.x; t < nu * rows_out; t += kW3 * 32) {
-    const int j = t / rows_out, i = t % rows_out;
-    int n0, n1;
-    float v0 = 0.f, v1 = 0.f, u0 = 0.f, u1 = 0.f;
+  if (e_on) {
+    float v0 = 0.f, v1 = 0.f, u0 = 0.f;
     if (kPairs) {
-      unit_rows<EPI>(a, u_begin + j, n0, n1);
-      const float* s0 = part + (size_t)(2 * j) * KS * R;
+      const float* s0 = part + (size_t)(2 * ej) * KS * R;
       const float* s1 = s0 + (size_t)KS * R;
-      for (int q = 0; q < KS; ++q) { v0 += s0[q * R + i]; v1 += s1[q * R + i]; }
-      gemv_epilogue<EPI>(a, i, n0, n1, true, v0, v1, 0.f, 0.f);
+      for (int q = 0; q < KS; ++q) { v0 += s0[q * R + ei]; v1 += s1[q * R + ei]; }
     } else {
-      n0 = u_begin + j; n1 = n0 + 1;
-      const float* s0 = part + (size_t)j * KS * R;
-      for (int q = 0; q < KS; ++q) { v0 += s0[q * R + i]; if (cfg) u0 += s0[q * R + a.B + i]; }
-      gemv_epilogue<EPI>(a, i, n0, n1, false, v0, v1, u0, u1);
+      const float* s0 = part + (size_t)ej * KS * R;
+      for (int q = 0; q < KS; ++q) { v0 += s0[q * R + ei]; if (cfg) u0 += s0[q * R + a.B + ei]; }
+    }
+    if (EPI == EPI_RESID) {
+      a.y[(size_t)ei * a.ldy + en0] = f2bf(pre_resid + rbf(v0));
+    } else if (EPI == EPI_QKV) {
+      const int qn_ = a.Hq * a.hd, kn_ = a.Hkv * a.hd;
+      float o0 = rbf(v0), o1 = rbf(v1);
+      if (en0 < qn_ + kn_) {                                 // same un-contracted fp32 ops as gemv_epilogue / _torch.py:57-68
+        const float r0 = __fsub_rn(__fmul_rn(o0, pre_cs.x), __fmul_rn(o1, pre_cs.y));
+        const float r1 = __fadd_rn(__fmul_rn(o1, pre_cs.x), __fmul_rn(o0, pre_cs.y));
+        o0 = r0; o1 = r1;
+      }
+      if (en0 < qn_) {
+        a.q_out[(size_t)ei * qn_ + en0] = f2bf(o0);
+        a.q_out[(size_t)ei * qn_ + en1] = f2bf(o1);
+      } else {
+        const int kvsel = en0 < qn_ + kn_ ? 0 : 1;
+        const int c0i = en0 - qn_ - kvsel * kn_, c1i = en1 - qn_ - kvsel * kn_;
+        bf16* pb = a.kv_layer + ((size_t)pre_page * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
+        const int tk = pre_pos % ZB_PAGE_TOKENS;
+        pb[((size_t)(c0i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c0i % a.hd)] = f2bf(o0);
+        pb[((size_t)(c1i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c1i % a.hd)] = f2bf(o1);
+      }
+    } else {
+      gemv_epilogue<EPI>(a, ei, en0, en1, kPairs, v0, v1, u0, 0.f);
     }
   }
 }
 
-// attention for one (row, kv head, split) unit by the consumer warps (warps 0..G-1 compute, all 16 load and sync)
 // K/V of the tokens cached by EARLIER steps for this CTA's first attention unit of the layer: issued before the
 // in_proj phase so the tile is already in shared memory when the attention phase starts
-__device__ __forceinline__ void mega_attention_prefetch(const MegaArgs& m, const bf16* kv_layer, int unit, int nunits, unsigned char* scratch) {
-  if (unit >= nunits) return;
+struct MegaAttnMeta { int n_old, page, g; };                  // step constants of this CTA's first attention unit
+__device__ __forceinline__ MegaAttnMeta mega_attention_meta(const MegaArgs& m, int unit, int nunits) {
+  MegaAttnMeta t; t.n_old = 0; t.page = 0; t.g = 0;
+  if (unit >= nunits) return t;
+  const int split = unit % m.nsplit, r = unit / (m.nsplit * m.Hkv);
+  t.g = (unit / m.nsplit) % m.Hkv;
+  const int kv_len = m.lengths[r] + 1;
+  t.n_old = max(0, min(kCH, kv_len - 1 - split * kCH));
+  if (t.n_old > 0) t.page = m.page_table[(size_t)r * m.max_pages + split];
+  return t;
+}
+__device__ __forceinline__ void mega_attention_prefetch(const MegaArgs& m, const bf16* kv_layer, const MegaAttnMeta& t, unsigned char* scratch) {
+  if (t.n_old <= 0) return;
   bf16* ks = reinterpret_cast<bf16*>(scratch);
   bf16* vs = ks + kCH * kKStride;
-  const int split = unit % m.nsplit, g = (unit / m.nsplit) % m.Hkv, r = unit / (m.nsplit * m.Hkv);
-  const int kv_len = m.lengths[r] + 1;
-  const int k0 = split * kCH;
-  const int n_old = min(kCH, kv_len - 1 - k0);
-  if (n_old <= 0) return;
-  const int page = m.page_table[(size_t)r * m.max_pages + split];
-  const bf16* kp = kv_layer + (((size_t)page * 2 + 0) * m.Hkv + g) * kCH * kHD;
-  const bf16* vp = kv_layer + (((size_t)page * 2 + 1) * m.Hkv + g) * kCH * kHD;
+  const bf16* kp = kv_layer + (((size_t)t.page * 2 + 0) * m.Hkv + t.g) * kCH * kHD;
+  const bf16* vp = kv_layer + (((size_t)t.page * 2 + 1) * m.Hkv + t.g) * kCH * kHD;
   for (int c = threadIdx.x; c < kCH * kHD / 8; c += kW3 * 32) {
     const int tok = c / (kHD / 8), d8 = (c % (kHD / 8)) * 8;
-    if (tok < n_old) {
+    if (tok < t.n_old) {
       cp_async16(ks + tok * kKStride + d8, kp + tok * kHD + d8);
       cp_async16(vs + tok * kHD + d8, vp + tok * kHD + d8);
     }
@@ -1006,18 +1051,18 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
     float* part = m.attn_part + (((size_t)r * m.Hq + head) * m.nsplit + split) * kPart;
     *reinterpret_cast<float4*>(part + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
     if (lane == 0) { part[kHD] = mx; part[kHD + 1] = l; }
-    __threadfence();
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
   if (threadIdx.x == 0) {
+    // one acq_rel RMW publishes this CTA's partials (cumulative over the CTA barrier) and acquires the others'
     int32_t* cnt = m.attn_counters + (size_t)r * m.Hkv + g;
-    const int prev = atomicAdd(cnt, 1);
+    int prev;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(prev) : "l"(cnt) : "memory");
     *s_last = (prev == nact - 1);
     if (*s_last) *cnt = 0;
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
   if (*s_last && warp < G) {
-    __threadfence();
     const float* base = m.attn_part + (((size_t)r * m.Hq + head) * m.nsplit) * kPart;
     float M = -INFINITY;
     for (int sp = 0; sp < nact; ++sp) M = fmaxf(M, __ldcg(base + (size_t)sp * kPart + kHD));
@@ -1090,6 +1135,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   // ===== consumers =====
   unsigned gen = 0;                                         // arrivals expected so far (the counter starts every step at 0)
   int gst = 0;
+  const MegaAttnMeta ameta = mega_attention_meta(m, blockIdx.x, R * m.Hkv * m.nsplit);
   int stamp_i = 0;
 #define MEGA_STAMP() do { if (m.timeline && blockIdx.x == 0 && threadIdx.x == 0 && stamp_i < 126) m.timeline[stamp_i] = gtime(); ++stamp_i; } while (0)
   MEGA_STAMP();
@@ -1116,7 +1162,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
     // A: norm -> in_proj -> RoPE -> KV append (+ q)
     mega_fill(a, m, R);
     a.W = L.in_proj; a.N = nqkv; a.K = m.D; a.x = m.x; a.ldx = m.D; a.nw = L.norm_w; a.nb = L.norm_b; a.kv_layer = L.kv_layer; a.q_out = m.q;
-    mega_attention_prefetch(m, L.kv_layer, blockIdx.x, R * m.Hkv * m.nsplit, attn_scratch);
+    mega_attention_prefetch(m, L.kv_layer, ameta, attn_scratch);
     mega_consume<R, 1, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane);
     MEGA_STAMP(); mega_grid_barrier(m.bar, gen); MEGA_STAMP();
     // B: attention over the paged cache
@@ -1540,6 +1586,10 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
   pb = std::max(pb, d.d_ff == 8192 ? part_need(d.d_model, false, d.d_ff, 2, 2) : part_need(d.d_model, false, d.d_ff, 1, 4));
   pb = std::max(pb, part_need(m.QV, false, d.d_model, 1, 4));
   pb = (pb + 1023) / 1024 * 1024;
+  {  // one epilogue item per consumer thread
+    const int max_items = std::max(((d.d_ff + grid - 1) / grid) * R, ((m.QV + grid - 1) / grid) * R);
+    ZB_REQUIRE(ctx, max_items <= kW3 * 32 && ((d.d_model + grid - 1) / grid) * R <= kW3 * 32, "persistent decode: %d epilogue items per CTA", max_items);
+  }
   const size_t attn_bytes = 40 * 1024;
   const size_t avail = 227 * 1024 - 2048;
   int stages = (int)((avail - pb - attn_bytes) / kMegaStageBytes);

@@ -230,38 +230,73 @@ def run_b200(args):
     ms_e, frames_e, _ = timed(step_e2e, args.steps)
     e2e = (frames_e / FRAME_RATE) / (ms_e / 1e3)
 
-    # ---- roofline leg: the dominant decode kernel (norm2 + fc1 + SiLU GEMV, 55 % of the weight bytes) timed ALONE
-    # with CUDA events, cycling over the layers so every launch streams its 67 MB from HBM (26 x 67 MB >> L2) ----
+    # ---- roofline leg.  The dominant kernel is the persistent decode step (decode_step_kernel: one launch per codec
+    # frame = embed + 26 layers + heads, > 95 % of the pass).  Its average launch duration is measured live with CUDA
+    # events as the slope of generate() time over the number of steps (two lengths, same prefill), which also contains
+    # the 1-CTA sampler launch that follows every step.  Algorithmic bytes per launch per SURVEY.md 8(d):
+    # W (3.2 GB, out_proj counted once - its slice is held in shared memory for both passes) + KV read + KV append. ----
     roof = None
+    breakdown = None
     if rank == 0:
         peak, peak_src = measured_peaks()
-        native = model._native_model()
-        sp = _lib.stream_ptr(dev)
-        R = 2 * B if 2 * B <= 8 else 8
-        iters = 8 * dims["n_layer"]
-        ctx.check(ctx.lib.zb_bench_kernel(ctx.handle, native, 0, 2, R, dims["n_layer"], sp))       # warm-up
-        torch.cuda.synchronize(dev)
+
+        def time_generate(n_frames, reps=2):
+            model.generate(cond_dev, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=5)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for r_ in range(reps):
+                c_ = model.generate(cond_dev, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=6 + r_)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps, c_
+
+        n_small = max(8, N // 8)
+        t_full, codes_full = time_generate(N)
+        t_small, _ = time_generate(n_small)
+        step_ms = (t_full - t_small) / (N - n_small)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        model.autoencoder.decode(codes_full)
         e0.record(stream)
-        ctx.check(ctx.lib.zb_bench_kernel(ctx.handle, native, 0, 2, R, iters, sp))                  # one C call, `iters` launches
+        for _ in range(3):
+            model.autoencoder.decode(codes_full)
         e1.record(stream)
         torch.cuda.synchronize(dev)
-        us = 1e3 * e0.elapsed_time(e1) / iters
-        fc1_bytes = 2 * dims["d_ff"] * dims["d_model"] * 2 + R * dims["d_model"] * 2 + R * dims["d_ff"] * 2 + 4 * dims["d_model"]
-        achieved = fc1_bytes / (us * 1e-6) / 1e9
-        # whole decode step, for context: algorithmic bytes per step over the measured step time
+        dac_ms = e0.elapsed_time(e1) / 3
         per_layer = (dims["n_heads"] + 2 * dims["n_heads_kv"]) * 128 * dims["d_model"] + dims["d_model"] ** 2 \
             + 3 * dims["d_ff"] * dims["d_model"]
         w_bytes = 2 * (dims["n_layer"] * per_layer + 9 * 1025 * dims["d_model"])
-        mean_s = Lc + 1 + (N + 8) / 2
-        kv_bytes = 2 * B * mean_s * dims["n_layer"] * 2 * dims["n_heads_kv"] * 128 * 2
-        step_bytes = w_bytes + kv_bytes
-        steps_per_utt = N + 8
-        roof = {"bound": "hbm", "kernel": "gemv_kernel<MT=%d, PRO_NORM, EPI_SILU> (norm2+fc1+SiLU)" % (2 if R <= 2 else 4 if R <= 4 else 8),
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "us_per_launch": us, "algorithmic_bytes_per_launch": fc1_bytes,
-                "decode_step": {"algorithmic_bytes": step_bytes, "ms_incl_prefill_and_dac": ms / args.steps / steps_per_utt,
-                                "achieved_gbs_lower_bound": step_bytes / (ms / args.steps / steps_per_utt * 1e-3) / 1e9}}
+        kv_tok = dims["n_layer"] * 2 * dims["n_heads_kv"] * 128 * 2
+        mean_s = Lc + 1 + (n_small + N + 16) / 2
+        step_bytes = w_bytes + 2 * B * mean_s * kv_tok + 2 * B * kv_tok + B * (9 * dims["d_model"] * 2 + 9 * 1025 * 4)
+        achieved = step_bytes / (step_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("decode_step_dram_bytes_per_launch")
+        native = model._native_model()
+        sp = _lib.stream_ptr(dev)
+        Rr = 2 * B if 2 * B <= 8 else 8
+        iters = 8 * dims["n_layer"]
+        ctx.check(ctx.lib.zb_bench_kernel(ctx.handle, native, 0, 2, Rr, dims["n_layer"], sp))
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.check(ctx.lib.zb_bench_kernel(ctx.handle, native, 0, 2, Rr, iters, sp))
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        fc1_us = 1e3 * e0.elapsed_time(e1) / iters
+        fc1_bytes = 2 * dims["d_ff"] * dims["d_model"] * 2 + Rr * dims["d_model"] * 2 + Rr * dims["d_ff"] * 2 + 4 * dims["d_model"]
+        roof = {"bound": "hbm", "kernel": "decode_step_kernel<R=%d> (persistent: embed + %d layers + heads, one launch per frame) + sample_kernel"
+                                          % (2 * B, dims["n_layer"]),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "us_per_launch": step_ms * 1e3, "algorithmic_bytes_per_launch": step_bytes,
+                "how": "slope of generate() time between %d and %d frames (CUDA events)" % (n_small, N),
+                "gemv_fc1_alone": {"kernel": "gemv3_kernel (norm2+fc1+SiLU), PDL-chained launches over all layers",
+                                   "us_per_launch": fc1_us, "achieved_gbs": fc1_bytes / (fc1_us * 1e-6) / 1e9,
+                                   "frac": fc1_bytes / (fc1_us * 1e-6) / 1e9 / peak}}
+        steps_full = N + 8
+        breakdown = {"decode_ms": step_ms * steps_full, "prefill_and_setup_ms": max(0.0, t_full - step_ms * steps_full), "dac_ms": dac_ms}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -277,7 +312,7 @@ def run_b200(args):
                 "data": "synthetic", "config": config_dict(args, n_gpus), "frames_per_second": frames / (ms / 1e3),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cond_host.numel() * 2, "d2h_bytes_per_step": wav_host.numel() * 4,
                         "ms_per_step": ms_e / args.steps},
-                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof, "breakdown_ms": breakdown, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

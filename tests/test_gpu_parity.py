@@ -226,6 +226,21 @@ def test_generate_batch_rows_are_independent():
         assert torch.equal(one[0], both[b])
 
 
+def test_generate_batch3_uses_dense_path_and_matches_oracle():
+    """B=3 (6 activation rows): decode runs through the tcgen05 GEMM path instead of the persistent GEMV kernel."""
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    model = build_b200_model(TINY_DIMS, w, DEV)
+    oracle = TransformerOracle(w, oracle_dims(TINY_DIMS), torch.bfloat16)
+    B, Lc, N = 3, 10, 12
+    cond = make_conditioning(2 * B, Lc, TINY_DIMS["d_model"], seed=9)
+    q = q_stream_from_seed(77, N + 9, B)
+    trace, otrace = {}, {}
+    codes = model.generate(cond.to(DEV), max_new_tokens=N, batch_size=B, q_stream=q, trace=trace)
+    ref = o_gen.generate(oracle, cond, None, N, 2.0, B, dict(min_p=0.1), q_stream=q, trace=otrace)
+    if check_generate_against_oracle(trace, otrace, dict(min_p=0.1), q, 0):
+        assert torch.equal(codes.cpu(), ref)
+
+
 # ------------------------------------------------------------------------------ DAC -------------
 def test_dac_decode_matches_reference_golden():
     """Waveform vs (a) the reference's CPU output (fp32, golden fixture) and (b) the oracle emulating the dtype flow of

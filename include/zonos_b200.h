@@ -78,9 +78,9 @@ typedef struct {
   /* Mamba2 only (mamba_ssm 2.2.5 Mamba2 parameter names) */
   const void* conv_w;           /* bf16 [conv_dim, d_conv] */
   const void* conv_b;           /* bf16 [conv_dim] */
-  const void* dt_bias;          /* fp32 [nheads] */
-  const void* A_log;            /* fp32 [nheads] */
-  const void* D;                /* fp32 [nheads] */
+  const void* dt_bias;          /* bf16 [nheads] (the module is cast to bf16, zonos/model.py:158) */
+  const void* A_log;            /* bf16 [nheads] */
+  const void* D;                /* bf16 [nheads] */
   const void* mnorm_w;          /* bf16 [d_inner] gated RMSNorm weight */
 } zb_layer;
 

@@ -12,10 +12,11 @@ All arithmetic of that path runs in `libzonos_b200.so` (hand-written CUDA behind
 from .autoencoder import DACAutoencoder
 from .backbone import BACKBONES, B200ZonosBackbone
 from .codebook_pattern import apply_delay_pattern, revert_delay_pattern
-from .config import BackboneConfig, InferenceParams, PrefixConditionerConfig, ZonosConfig, transformer_config_dict
+from .config import (BackboneConfig, InferenceParams, PrefixConditionerConfig, ZonosConfig, hybrid_config_dict,
+                     transformer_config_dict)
 from .model import Zonos
 from .sampling import sample_from_logits
 
 __all__ = ["Zonos", "ZonosConfig", "BackboneConfig", "PrefixConditionerConfig", "InferenceParams", "BACKBONES",
            "B200ZonosBackbone", "DACAutoencoder", "sample_from_logits", "apply_delay_pattern", "revert_delay_pattern",
-           "transformer_config_dict"]
+           "transformer_config_dict", "hybrid_config_dict"]

@@ -39,25 +39,65 @@ class _MLP(nn.Module):
         self.fc2 = nn.Linear(d_ff, d_model, bias=False)
 
 
-class _Block(nn.Module):
-    def __init__(self, cfg: BackboneConfig):
+class _Weight(nn.Module):
+    def __init__(self, n):
         super().__init__()
-        heads, heads_kv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
+        self.weight = nn.Parameter(torch.ones(n))
+
+
+class _Mamba2Mixer(nn.Module):
+    """Parameter holder with mamba_ssm's Mamba2 names and shapes (defaults of ssm_cfg={"layer": "Mamba2"}:
+    d_state 128, d_conv 4, expand 2, headdim 64, ngroups 1)."""
+
+    def __init__(self, d_model, ssm_cfg: dict):
+        super().__init__()
+        self.d_state = ssm_cfg.get("d_state", 128)
+        self.d_conv = ssm_cfg.get("d_conv", 4)
+        self.headdim = ssm_cfg.get("headdim", 64)
+        self.ngroups = ssm_cfg.get("ngroups", 1)
+        self.d_inner = ssm_cfg.get("expand", 2) * d_model
+        self.nheads = self.d_inner // self.headdim
+        conv_dim = self.d_inner + 2 * self.ngroups * self.d_state
+        self.in_proj = nn.Linear(d_model, 2 * self.d_inner + 2 * self.ngroups * self.d_state + self.nheads, bias=False)
+        self.conv1d = nn.Conv1d(conv_dim, conv_dim, self.d_conv, groups=conv_dim, padding=self.d_conv - 1, bias=True)
+        self.dt_bias = nn.Parameter(torch.zeros(self.nheads))
+        self.A_log = nn.Parameter(torch.zeros(self.nheads))
+        self.D = nn.Parameter(torch.ones(self.nheads))
+        self.norm = _Weight(self.d_inner)
+        self.out_proj = nn.Linear(self.d_inner, d_model, bias=False)
+
+
+class _Block(nn.Module):
+    def __init__(self, cfg: BackboneConfig, is_attention: bool = True):
+        super().__init__()
+        self.is_attention = is_attention
         self.norm = nn.LayerNorm(cfg.d_model, eps=cfg.norm_epsilon)
-        self.mixer = _Mixer(cfg.d_model, heads, heads_kv, cfg.d_model // heads)
-        self.norm2 = nn.LayerNorm(cfg.d_model, eps=cfg.norm_epsilon)
-        self.mlp = _MLP(cfg.d_model, cfg.attn_mlp_d_intermediate)
+        if is_attention:
+            heads, heads_kv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
+            self.mixer = _Mixer(cfg.d_model, heads, heads_kv, cfg.d_model // heads)
+            self.norm2 = nn.LayerNorm(cfg.d_model, eps=cfg.norm_epsilon)
+            self.mlp = _MLP(cfg.d_model, cfg.attn_mlp_d_intermediate)
+        else:
+            assert cfg.d_intermediate == 0, "Mamba2 layers with an MLP (d_intermediate > 0) are not supported"
+            self.mixer = _Mamba2Mixer(cfg.d_model, cfg.ssm_cfg)
 
 
 class PagedKVCache:
     """Caller-owned paged KV memory in the layout include/zonos_b200.h documents."""
 
-    def __init__(self, n_attn_layers, rows, max_seqlen, n_heads_kv, head_dim, device, dtype=torch.bfloat16):
+    def __init__(self, n_attn_layers, rows, max_seqlen, n_heads_kv, head_dim, device, dtype=torch.bfloat16, mamba=None):
         P = _lib.PAGE_TOKENS
         self.rows = rows
         self.pages_per_row = (max_seqlen + P - 1) // P
         self.num_pages = rows * self.pages_per_row
-        self.kv_pages = torch.empty(n_attn_layers, self.num_pages, 2, n_heads_kv, P, head_dim, dtype=dtype, device=device)
+        self.kv_pages = torch.empty(max(n_attn_layers, 1), self.num_pages, 2, n_heads_kv, P, head_dim, dtype=dtype, device=device)
+        # Mamba2 layers: rolling conv window [n_mamba, R, conv_dim, d_conv] and SSM state [n_mamba, R, nheads, headdim, d_state],
+        # zero-initialised like mamba_ssm's allocate_inference_cache
+        self.conv_state = self.ssm_state = None
+        if mamba is not None:
+            n_mamba, conv_dim, d_conv, nheads, headdim, d_state = mamba
+            self.conv_state = torch.zeros(n_mamba, rows, conv_dim, d_conv, dtype=dtype, device=device)
+            self.ssm_state = torch.zeros(n_mamba, rows, nheads, headdim, d_state, dtype=dtype, device=device)
         # simplest allocation policy: row r owns pages [r*ppr, (r+1)*ppr); the kernels only ever go through the table
         self.page_table = torch.arange(self.num_pages, dtype=torch.int32, device=device).view(rows, self.pages_per_row).contiguous()
 
@@ -66,22 +106,28 @@ class PagedKVCache:
         d = _lib.zb_cache()
         d.rows, d.num_pages, d.max_pages_per_row = self.rows, self.num_pages, self.pages_per_row
         d.kv_pages, d.page_table, d.lengths = self.kv_pages.data_ptr(), self.page_table.data_ptr(), lengths.data_ptr()
-        d.conv_state = d.ssm_state = None
+        d.conv_state = self.conv_state.data_ptr() if self.conv_state is not None else None
+        d.ssm_state = self.ssm_state.data_ptr() if self.ssm_state is not None else None
         return d
 
 
 class B200ZonosBackbone(nn.Module):
-    supported_architectures = ["transformer"]
+    supported_architectures = ["transformer", "hybrid"]
 
     def __init__(self, config: BackboneConfig):
-        assert not config.ssm_cfg, "the hybrid (Mamba2) layers are not built yet in this round"
         super().__init__()
         self.config = config
-        self.layers = nn.ModuleList(_Block(config) for _ in range(config.n_layer))
+        self.hybrid = bool(config.ssm_cfg)
+        if self.hybrid:
+            assert config.ssm_cfg.get("layer", "Mamba2") == "Mamba2", "only Mamba2 SSM layers are supported"
+        attn = set(config.attn_layer_idx) if self.hybrid else set(range(config.n_layer))
+        self.layers = nn.ModuleList(_Block(config, i in attn) for i in range(config.n_layer))
         self.norm_f = nn.LayerNorm(config.d_model, eps=config.norm_epsilon)
-        # reference quirks kept as switches: _torch.py applies out_proj twice and rotates interleaved pairs
-        self.out_proj_repeats = 2
-        self.rope_interleaved = True
+        # Reference quirks kept as switches.  Transformer variant = zonos/backbone/_torch.py: out_proj applied
+        # twice, interleaved-pair RoPE with an fp32 table, LayerNorm.  Hybrid variant = mamba_ssm blocks
+        # (zonos/backbone/_mamba_ssm.py): out_proj once, rotate-half RoPE with cos/sin cached in bf16, norm per `rms_norm`.
+        self.out_proj_repeats = 1 if self.hybrid else 2
+        self.rope_interleaved = not self.hybrid
         self._native = None       # (key, handle, keepalive)
         self._cache: PagedKVCache | None = None
 
@@ -105,20 +151,31 @@ class B200ZonosBackbone(nn.Module):
         H, Hkv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
         hd = cfg.d_model // H
         rope = rotary_table(ROPE_TABLE_LEN, hd, device=p0.device)
+        if self.hybrid:      # flash_attn RotaryEmbedding keeps cos/sin in the activation dtype
+            rope = rope.to(torch.bfloat16).float().contiguous()
         layers = (_lib.zb_layer * cfg.n_layer)()
+        mm = None
         for i, blk in enumerate(self.layers):
             L = layers[i]
-            L.kind = 0
+            L.kind = 0 if blk.is_attention else 1
             L.norm_w, L.norm_b = blk.norm.weight.data_ptr(), blk.norm.bias.data_ptr()
             L.in_proj, L.out_proj = blk.mixer.in_proj.weight.data_ptr(), blk.mixer.out_proj.weight.data_ptr()
-            L.norm2_w, L.norm2_b = blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr()
-            L.fc1, L.fc2 = blk.mlp.fc1.weight.data_ptr(), blk.mlp.fc2.weight.data_ptr()
+            if blk.is_attention:
+                L.norm2_w, L.norm2_b = blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr()
+                L.fc1, L.fc2 = blk.mlp.fc1.weight.data_ptr(), blk.mlp.fc2.weight.data_ptr()
+            else:
+                mm = blk.mixer
+                L.conv_w, L.conv_b = mm.conv1d.weight.data_ptr(), mm.conv1d.bias.data_ptr()
+                L.dt_bias, L.A_log, L.D = mm.dt_bias.data_ptr(), mm.A_log.data_ptr(), mm.D.data_ptr()
+                L.mnorm_w = mm.norm.weight.data_ptr()
         d = _lib.zb_model_desc()
         d.d_model, d.n_layer, d.n_heads, d.n_heads_kv, d.head_dim = cfg.d_model, cfg.n_layer, H, Hkv, hd
         d.d_ff = cfg.attn_mlp_d_intermediate
         d.n_codebooks, d.head_vocab = n_codebooks, head_vocab
         d.emb_vocab = embeddings[0].shape[0] if embeddings else 0
-        d.norm_kind = 0
+        d.norm_kind = 1 if (self.hybrid and cfg.rms_norm) else 0        # _torch.py ignores rms_norm (LayerNorm always)
+        if mm is not None:
+            d.d_inner, d.d_state, d.d_conv, d.m_headdim, d.m_ngroups = mm.d_inner, mm.d_state, mm.d_conv, mm.headdim, mm.ngroups
         d.rope_interleaved, d.out_proj_repeats = int(self.rope_interleaved), self.out_proj_repeats
         d.norm_eps, d.rope_len, d.rope_table = cfg.norm_epsilon, ROPE_TABLE_LEN, rope.data_ptr()
         d.layers = layers
@@ -142,8 +199,16 @@ class B200ZonosBackbone(nn.Module):
         cfg = self.config
         H, Hkv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
         device = next(self.parameters()).device
-        self._cache = PagedKVCache(cfg.n_layer, batch_size, max_seqlen, Hkv, cfg.d_model // H, device, dtype)
-        return {i: (self._cache.kv_pages[i], self._cache.page_table) for i in range(cfg.n_layer)}
+        attn_layers = [i for i, b in enumerate(self.layers) if b.is_attention]
+        mamba_layers = [i for i, b in enumerate(self.layers) if not b.is_attention]
+        mamba = None
+        if mamba_layers:
+            mm = self.layers[mamba_layers[0]].mixer
+            mamba = (len(mamba_layers), mm.d_inner + 2 * mm.ngroups * mm.d_state, mm.d_conv, mm.nheads, mm.headdim, mm.d_state)
+        self._cache = PagedKVCache(len(attn_layers), batch_size, max_seqlen, Hkv, cfg.d_model // H, device, dtype, mamba=mamba)
+        out = {i: (self._cache.kv_pages[a], self._cache.page_table) for a, i in enumerate(attn_layers)}
+        out.update({i: (self._cache.conv_state[m], self._cache.ssm_state[m]) for m, i in enumerate(mamba_layers)})
+        return out
 
     def forward(self, hidden_states: torch.Tensor, inference_params: InferenceParams, last_only: bool = False) -> torch.Tensor:
         """zonos/backbone/_torch.py:213-238.  Positions come from `inference_params.lengths_per_sample`."""

@@ -76,3 +76,17 @@ def transformer_config_dict(d_model=2048, n_layer=26, n_heads=16, n_heads_kv=4, 
                       rms_norm=False, residual_in_fp32=False, norm_epsilon=1e-5),
         prefix_conditioner=dict(projection="linear", conditioners=conditioners if conditioners is not None else []),
         eos_token_id=1024, masked_token_id=1025)
+
+
+def hybrid_config_dict(d_model=2048, n_layer=46, attn_layer_idx=(9, 18, 27, 36, 45), n_heads=16, n_heads_kv=4, d_ff=8192,
+                       rms_norm=False, conditioners=None) -> dict:
+    """Zonos-v0.1-hybrid shape.  The hybrid config.json is NOT in the reference tree; n_layer / attn_layer_idx here are the
+    assumption stated in SURVEY.md 8(c) - everything stays parameterised by BackboneConfig (zonos/config.py:75-84)."""
+    return dict(
+        backbone=dict(d_model=d_model, d_intermediate=0, attn_mlp_d_intermediate=d_ff, n_layer=n_layer, ssm_cfg={"layer": "Mamba2"},
+                      attn_layer_idx=list(attn_layer_idx),
+                      attn_cfg=dict(causal=True, num_heads=n_heads, num_heads_kv=n_heads_kv, rotary_emb_dim=128,
+                                    qkv_proj_bias=False, out_proj_bias=False),
+                      rms_norm=rms_norm, residual_in_fp32=False, norm_epsilon=1e-5),
+        prefix_conditioner=dict(projection="linear", conditioners=conditioners if conditioners is not None else []),
+        eos_token_id=1024, masked_token_id=1025)

@@ -1240,9 +1240,131 @@ __global__ void __launch_bounds__(256) norm_kernel(NormArgs a) {
     dst[k] = f2bf((bf2f(src[k]) - mean) * rstd * bf2f(a.w[k]) + (a.b ? bf2f(a.b[k]) : 0.f));
 }
 
+
+// ------------------------------------------------------------------ Mamba2: conv1d step + selective state update ---
+// Replaces mamba_ssm's causal_conv1d_update / causal_conv1d_fn + selective_state_update / mamba_chunk_scan_combined
+// (reached from zonos/backbone/_mamba_ssm.py:45-58; recurrence in SURVEY.md Appendix C) for T >= 1 tokens per row.
+// grid (rows, nheads), 256 threads: thread (p = tid/4, quarter = tid%4) owns 32 of the 128 states of head dimension p
+// in fp32 registers for the whole token loop, so the 16 KB-per-head SSM state is read and written exactly once per
+// call; the depthwise conv window of the head's 64 x-channels and of the shared B/C channels lives in shared memory.
+// Decode (T == 1) stores the state in the cache dtype every step like selective_state_update; prefill rounds only the
+// final state like the chunked scan.  Output: g = bf16(y) * silu(z) in fp32 (input of the gated RMSNorm).
+struct ScanArgs {
+  const bf16* zx;           // [M, in_proj_out] rows z | xBC | dt
+  int T, d_inner, d_state, d_conv, headdim, nheads, ngroups, in_proj_out, conv_dim;
+  const bf16 *conv_w, *conv_b, *dt_bias, *A_log, *Dp;
+  bf16* conv_state;         // [rows, conv_dim, d_conv]
+  bf16* ssm_state;          // [rows, nheads, headdim, d_state]
+  float* g;                 // [M, d_inner]
+  const zb_loop_state* loop; int T_delayed;
+};
+
+__global__ void __launch_bounds__(256) mamba_scan_kernel(ScanArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (loop_idle(a.loop, a.T_delayed)) return;
+  constexpr int P = 64, N = 128, DC = 4;                       // headdim, d_state, d_conv (checked on the host)
+  constexpr int CH = P + 2 * N;                                // channels this CTA convolves: its 64 x + B + C
+  __shared__ float win[CH][DC];                                // rolling window, oldest first
+  __shared__ float cw[CH][DC];
+  __shared__ float cb[CH];
+  __shared__ float cout[CH];
+  const int r = blockIdx.x, hh = blockIdx.y, tid = threadIdx.x;
+  const int p = tid >> 2, quarter = tid & 3;
+  auto chan = [&](int c) { return c < P ? hh * P + c : a.d_inner + (c - P); };   // index into xBC / conv_state
+  for (int c = tid; c < CH; c += 256) {
+    const int gc = chan(c);
+    for (int j = 0; j < DC; ++j) {
+      win[c][j] = bf2f(a.conv_state[((size_t)r * a.conv_dim + gc) * DC + j]);
+      cw[c][j] = bf2f(a.conv_w[(size_t)gc * DC + j]);
+    }
+    cb[c] = bf2f(a.conv_b[gc]);
+  }
+  float h[32];
+  {
+    const bf16* sp = a.ssm_state + (((size_t)r * a.nheads + hh) * P + p) * N + quarter * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sp + j);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { h[j + 2 * q] = bf16lo(w4[q]); h[j + 2 * q + 1] = bf16hi(w4[q]); }
+    }
+  }
+  const float A = -expf(bf2f(a.A_log[hh])), Dv = bf2f(a.Dp[hh]), dtb = bf2f(a.dt_bias[hh]);
+  __syncthreads();
+  for (int t = 0; t < a.T; ++t) {
+    const bf16* row = a.zx + ((size_t)r * a.T + t) * a.in_proj_out;
+    for (int c = tid; c < CH; c += 256) {
+      const float xin = bf2f(row[a.d_inner + chan(c)]);
+      float acc = cb[c];
+#pragma unroll
+      for (int j = 0; j < DC - 1; ++j) { win[c][j] = win[c][j + 1]; acc = fmaf(win[c][j], cw[c][j], acc); }
+      win[c][DC - 1] = xin;
+      acc = fmaf(xin, cw[c][DC - 1], acc);
+      cout[c] = rbf(acc / (1.0f + expf(-acc)));               // SiLU, output in the activation dtype
+    }
+    __syncthreads();
+    const float dtr = bf2f(row[a.d_inner + a.conv_dim + hh]) + dtb;
+    const float dt = dtr > 20.0f ? dtr : log1pf(expf(dtr));      // softplus (F.softplus threshold 20)
+    const float dA = expf(dt * A);
+    const float xp = cout[p], dtx = dt * xp;
+    float yacc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = quarter * 32 + j;
+      h[j] = fmaf(h[j], dA, dtx * cout[P + n]);
+      yacc = fmaf(h[j], cout[P + N + n], yacc);
+      if (a.T == 1) h[j] = rbf(h[j]);                            // decode: the stored state is in the cache dtype
+    }
+    yacc += __shfl_xor_sync(0xffffffffu, yacc, 1);
+    yacc += __shfl_xor_sync(0xffffffffu, yacc, 2);
+    if (quarter == 0) {
+      const float y = rbf(yacc + Dv * xp);
+      const float z = bf2f(row[hh * P + p]);
+      a.g[((size_t)r * a.T + t) * a.d_inner + hh * P + p] = y * (z / (1.0f + expf(-z)));
+    }
+    __syncthreads();
+  }
+  {
+    bf16* sp = a.ssm_state + (((size_t)r * a.nheads + hh) * P + p) * N + quarter * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 v;
+      v.x = pack_bf16(h[j], h[j + 1]); v.y = pack_bf16(h[j + 2], h[j + 3]); v.z = pack_bf16(h[j + 4], h[j + 5]); v.w = pack_bf16(h[j + 6], h[j + 7]);
+      *reinterpret_cast<uint4*>(sp + j) = v;
+    }
+  }
+  for (int c = tid; c < CH; c += 256) {
+    if (c >= P && hh != 0) continue;                              // the shared B/C channels are written once (head 0)
+    const int gc = chan(c);
+    for (int j = 0; j < DC; ++j) a.conv_state[((size_t)r * a.conv_dim + gc) * DC + j] = f2bf(win[c][j]);
+  }
+}
+
+// gated RMSNorm of mamba_ssm (RMSNormGated, norm_before_gate=False): xn = bf16(g * rsqrt(mean(g^2) + eps) * w)
+struct GNormArgs { const float* g; bf16* y; const bf16* w; int D; float eps; const zb_loop_state* loop; int T_delayed; };
+__global__ void __launch_bounds__(256) gated_norm_kernel(GNormArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (loop_idle(a.loop, a.T_delayed)) return;
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* src = a.g + (size_t)blockIdx.x * a.D;
+  float sq = 0.f;
+  for (int k = threadIdx.x; k < a.D; k += 256) { const float v = src[k]; sq = fmaf(v, v, sq); }
+  sq = warp_sum(sq);
+  if (lane == 0) red[warp] = sq;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float rstd = rsqrtf(tot / (float)a.D + a.eps);
+  for (int k = threadIdx.x; k < a.D; k += 256) a.y[(size_t)blockIdx.x * a.D + k] = f2bf(src[k] * rstd * bf2f(a.w[k]));
+}
+
 // ------------------------------------------------------------------ host side ----------------
 struct Scratch {
-  bf16 *q, *attn_y, *y1, *h, *xn; float* part; int32_t* counters; int nsplit;
+  bf16 *q, *attn_y, *y1, *h, *xn, *zx, *gn; float *part, *g; int32_t* counters; int nsplit;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1255,12 +1377,14 @@ Scratch carve(const zb_model* mdl, void* base, int M, int nsplit, size_t* total)
   size_t o_q = take((size_t)M * qn * 2), o_ay = take((size_t)M * qn * 2), o_y1 = take((size_t)M * d.d_model * 2);
   size_t o_h = take((size_t)M * d.d_ff * 2);
   size_t o_xn = take((size_t)M * d.d_model * 2);
+  const size_t ipo = (size_t)2 * d.d_inner + 2 * d.m_ngroups * d.d_state + (d.m_headdim ? d.d_inner / d.m_headdim : 0);
+  size_t o_zx = take((size_t)M * ipo * 2), o_g = take((size_t)M * d.d_inner * 4), o_gn = take((size_t)M * d.d_inner * 2);
   size_t o_part = take((size_t)M * d.n_heads * nsplit * kPart * 4);
   if (total) *total = off;
   Scratch s{};
   if (base) {
     char* b = (char*)base;
-    s.q = (bf16*)(b + o_q); s.attn_y = (bf16*)(b + o_ay); s.y1 = (bf16*)(b + o_y1); s.h = (bf16*)(b + o_h); s.xn = (bf16*)(b + o_xn);
+    s.q = (bf16*)(b + o_q); s.attn_y = (bf16*)(b + o_ay); s.y1 = (bf16*)(b + o_y1); s.h = (bf16*)(b + o_h); s.xn = (bf16*)(b + o_xn); s.zx = (bf16*)(b + o_zx); s.g = (float*)(b + o_g); s.gn = (bf16*)(b + o_gn);
     s.part = (float*)(b + o_part);
   }
   s.nsplit = nsplit;
@@ -1382,7 +1506,7 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
   const zb_model_desc& d = model->d;
   const int M = R * T;
   ZB_REQUIRE(ctx, d.head_dim == kHD, "head_dim %d unsupported (128 only)", d.head_dim);
-  ZB_REQUIRE(ctx, d.n_heads % d.n_heads_kv == 0 && d.n_heads / d.n_heads_kv <= 8, "GQA group size unsupported");
+  ZB_REQUIRE(ctx, d.n_heads_kv > 0 && d.n_heads % d.n_heads_kv == 0 && d.n_heads / d.n_heads_kv <= 8, "GQA group size unsupported");
   ZB_REQUIRE(ctx, cache && cache->rows >= R, "cache has %d rows, need %d", cache ? cache->rows : 0, R);
   const int nsplit = (max_kv_len + kCH - 1) / kCH;
   ZB_REQUIRE(ctx, nsplit <= cache->max_pages_per_row, "sequence of %d tokens exceeds the page table (%d pages)", max_kv_len,
@@ -1397,7 +1521,8 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
   const int qn = d.n_heads * d.head_dim;
   const int G = d.n_heads / d.n_heads_kv;
 
-  const bool tc = M > 4 && d.rope_interleaved && d.d_model % 64 == 0 && d.d_ff % 64 == 0;   // dense path: tcgen05 GEMMs
+  const bool tc = M > 4 && d.d_model % 64 == 0 && d.d_ff % 64 == 0;   // dense path: tcgen05 GEMMs
+  const bool tc_qkv = tc && d.rope_interleaved;                     // (the tcgen05 QKV epilogue rotates interleaved pairs only)
   auto norm_rows = [&](const bf16* w, const bf16* b) -> zb_status {
     NormArgs na;
     na.x = x; na.ldx = d.d_model; na.y = s.xn; na.ldy = d.d_model; na.w = w; na.b = b; na.D = d.d_model; na.eps = d.norm_eps; na.kind = d.norm_kind;
@@ -1407,11 +1532,56 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
   };
   for (int li = 0; li < d.n_layer; ++li) {
     const zb_layer& L = model->layers[li];
-    ZB_REQUIRE(ctx, L.kind == ZB_LAYER_ATTENTION, "layer %d: only attention layers are implemented in this build", li);
-    bf16* kv_layer = (bf16*)cache->kv_pages + (size_t)model->attn_index[li] * cache->num_pages * page_elems;
     GemvArgs a;
+    if (L.kind == ZB_LAYER_MAMBA2) {
+      // ---- Mamba2 layer: norm -> in_proj -> conv1d step + selective state update -> gated RMSNorm -> out_proj + residual
+      const int nheads = d.d_inner / d.m_headdim, conv_dim = d.d_inner + 2 * d.m_ngroups * d.d_state;
+      const int ipo = 2 * d.d_inner + 2 * d.m_ngroups * d.d_state + nheads;
+      ZB_REQUIRE(ctx, d.m_headdim == 64 && d.d_state == 128 && d.d_conv == 4 && d.m_ngroups == 1, "Mamba2: only headdim 64, d_state 128, d_conv 4, ngroups 1");
+      ZB_REQUIRE(ctx, cache->conv_state && cache->ssm_state, "Mamba2 layer %d: the cache has no conv/ssm state", li);
+      const int mi = model->mamba_index[li];
+      if (tc) {
+        if (zb_status st = norm_rows((const bf16*)L.norm_w, (const bf16*)L.norm_b)) return st;
+        zb_gemm_tc g;
+        g.W = (const bf16*)L.in_proj; g.x = s.xn; g.ldx = d.d_model; g.M = M; g.N = ipo; g.K = d.d_model; g.epi = 0; g.y = s.zx; g.ldy = ipo;
+        if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
+      } else {
+        memset(&a, 0, sizeof(a));
+        a.W = (const bf16*)L.in_proj; a.x = x; a.ldx = d.d_model; a.M = M; a.N = ipo; a.K = d.d_model;
+        a.nw = (const bf16*)L.norm_w; a.nb = (const bf16*)L.norm_b; a.eps = d.norm_eps; a.norm_kind = d.norm_kind;
+        a.y = s.zx; a.ldy = ipo; a.loop = loop; a.T_delayed = T_delayed;
+        if (zb_status st = launch_gemv<PRO_NORM, EPI_STORE>(ctx, a, stream)) return st;
+      }
+      ScanArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      sa.zx = s.zx; sa.T = T; sa.d_inner = d.d_inner; sa.d_state = d.d_state; sa.d_conv = d.d_conv; sa.headdim = d.m_headdim; sa.nheads = nheads;
+      sa.ngroups = d.m_ngroups; sa.in_proj_out = ipo; sa.conv_dim = conv_dim;
+      sa.conv_w = (const bf16*)L.conv_w; sa.conv_b = (const bf16*)L.conv_b; sa.dt_bias = (const bf16*)L.dt_bias; sa.A_log = (const bf16*)L.A_log; sa.Dp = (const bf16*)L.D;
+      sa.conv_state = (bf16*)cache->conv_state + (size_t)mi * cache->rows * conv_dim * d.d_conv;
+      sa.ssm_state = (bf16*)cache->ssm_state + (size_t)mi * cache->rows * nheads * d.m_headdim * d.d_state;
+      sa.g = s.g; sa.loop = loop; sa.T_delayed = T_delayed;
+      ZB_CUDA(ctx, zb_launch_pdl(mamba_scan_kernel, dim3(R, nheads), dim3(256), 0, stream, sa));
+      ctx->launches++;
+      GNormArgs ga;
+      ga.g = s.g; ga.y = s.gn; ga.w = (const bf16*)L.mnorm_w; ga.D = d.d_inner; ga.eps = 1e-5f; ga.loop = loop; ga.T_delayed = T_delayed;
+      ZB_CUDA(ctx, zb_launch_pdl(gated_norm_kernel, dim3(M), dim3(256), 0, stream, ga));
+      ctx->launches++;
+      if (tc && d.d_inner % 64 == 0) {
+        zb_gemm_tc g;
+        g.W = (const bf16*)L.out_proj; g.x = s.gn; g.ldx = d.d_inner; g.M = M; g.N = d.d_model; g.K = d.d_inner;
+        g.epi = 1; g.y = x; g.ldy = d.d_model; g.resid = x; g.ldr = d.d_model;
+        if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
+      } else {
+        memset(&a, 0, sizeof(a));
+        a.W = (const bf16*)L.out_proj; a.x = s.gn; a.ldx = d.d_inner; a.M = M; a.N = d.d_model; a.K = d.d_inner;
+        a.y = x; a.ldy = d.d_model; a.resid = x; a.ldr = d.d_model; a.loop = loop; a.T_delayed = T_delayed;
+        if (zb_status st = launch_gemv<PRO_NONE, EPI_RESID>(ctx, a, stream)) return st;
+      }
+      continue;
+    }
+    bf16* kv_layer = (bf16*)cache->kv_pages + (size_t)model->attn_index[li] * cache->num_pages * page_elems;
     // 1. norm -> in_proj -> RoPE -> KV append (+ q)
-    if (tc) {
+    if (tc_qkv) {
       if (zb_status st = norm_rows((const bf16*)L.norm_w, (const bf16*)L.norm_b)) return st;
       zb_gemm_tc g;
       g.W = (const bf16*)L.in_proj; g.x = s.xn; g.ldx = d.d_model; g.M = M; g.N = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim; g.K = d.d_model;
@@ -1545,6 +1715,7 @@ bool zb_mega_supported(const zb_model* model, int R) {
   static const int enabled = env_int("ZB_DECODE_MEGA", 1);
   auto k_ok = [](int K) { return K == 256 || K == 512 || K == 1024 || K == 2048 || K == 4096; };
   const int qn = d.n_heads * d.head_dim;
+  if (model->n_mamba > 0) return false;                       // hybrid stacks use the multi-kernel graph path
   return enabled && R >= 2 && R <= 4 && d.head_dim == kHD && k_ok(d.d_model) && k_ok(qn) && (k_ok(d.d_ff) || d.d_ff == 8192) &&
          d.n_codebooks <= 16 && d.n_heads / d.n_heads_kv <= 8 && (d.out_proj_repeats == 1 || qn == d.d_model) &&
          d.out_proj_repeats >= 1 && d.out_proj_repeats <= 2 && (((d.n_heads + 2 * d.n_heads_kv) * d.head_dim) % 2 == 0);

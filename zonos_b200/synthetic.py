@@ -91,3 +91,46 @@ def make_conditioning(rows: int, cond_len: int, d_model: int, seed=1234) -> torc
     """bf16 [rows, cond_len, d_model] ~ N(0,1): the post-LayerNorm scale of zonos/conditioning.py:522."""
     g = torch.Generator().manual_seed(seed)
     return torch.randn(rows, cond_len, d_model, generator=g).bfloat16()
+
+
+HYBRID_TINY_DIMS = dict(d_model=512, n_layer=4, attn_layer_idx=(2,), n_heads=4, n_heads_kv=2, d_ff=1024)
+
+
+def make_hybrid_weights(d_model=2048, n_layer=46, attn_layer_idx=(9, 18, 27, 36, 45), n_heads=16, n_heads_kv=4, d_ff=8192,
+                        d_state=128, d_conv=4, expand=2, m_headdim=64, ngroups=1, n_codebooks=9, head_vocab=1025, emb_vocab=1032,
+                        seed=0, dtype=torch.bfloat16, heads_scale=1.0) -> dict:
+    """Hybrid (Mamba2 + attention) backbone with mamba_ssm's parameter names (`mixer.in_proj/conv1d/dt_bias/A_log/D/norm/
+    out_proj` for Mamba2 layers; attention layers as in the transformer variant) and its default initialisers' scales."""
+    g = torch.Generator().manual_seed(seed)
+    hd = d_model // n_heads
+    d_inner = expand * d_model
+    nheads = d_inner // m_headdim
+    conv_dim = d_inner + 2 * ngroups * d_state
+    w = {}
+    for i in range(n_layer):
+        p = f"backbone.layers.{i}."
+        w[p + "norm.weight"] = (1.0 + 0.1 * torch.randn(d_model, generator=g)).to(dtype)
+        w[p + "norm.bias"] = (0.05 * torch.randn(d_model, generator=g)).to(dtype)
+        if i in attn_layer_idx:
+            w[p + "mixer.in_proj.weight"] = _uniform(g, ((n_heads + 2 * n_heads_kv) * hd, d_model), 1 / math.sqrt(d_model), dtype)
+            w[p + "mixer.out_proj.weight"] = _uniform(g, (d_model, n_heads * hd), 1 / math.sqrt(n_heads * hd), dtype)
+            w[p + "norm2.weight"] = (1.0 + 0.1 * torch.randn(d_model, generator=g)).to(dtype)
+            w[p + "norm2.bias"] = (0.05 * torch.randn(d_model, generator=g)).to(dtype)
+            w[p + "mlp.fc1.weight"] = _uniform(g, (2 * d_ff, d_model), 1 / math.sqrt(d_model), dtype)
+            w[p + "mlp.fc2.weight"] = _uniform(g, (d_model, d_ff), 1 / math.sqrt(d_ff), dtype)
+        else:
+            w[p + "mixer.in_proj.weight"] = _uniform(g, (2 * d_inner + 2 * ngroups * d_state + nheads, d_model), 1 / math.sqrt(d_model), dtype)
+            w[p + "mixer.conv1d.weight"] = _uniform(g, (conv_dim, 1, d_conv), 1 / math.sqrt(d_conv), dtype)
+            w[p + "mixer.conv1d.bias"] = _uniform(g, (conv_dim,), 1 / math.sqrt(d_conv), dtype)
+            dt = torch.exp(torch.rand(nheads, generator=g) * (math.log(0.1) - math.log(0.001)) + math.log(0.001)).clamp(min=1e-4)
+            w[p + "mixer.dt_bias"] = (dt + torch.log(-torch.expm1(-dt))).to(dtype)          # inverse softplus
+            w[p + "mixer.A_log"] = torch.log(1 + 15 * torch.rand(nheads, generator=g)).to(dtype)
+            w[p + "mixer.D"] = torch.ones(nheads).to(dtype)
+            w[p + "mixer.norm.weight"] = (1.0 + 0.1 * torch.randn(d_inner, generator=g)).to(dtype)
+            w[p + "mixer.out_proj.weight"] = _uniform(g, (d_model, d_inner), 1 / math.sqrt(d_inner), dtype)
+    w["backbone.norm_f.weight"] = (1.0 + 0.1 * torch.randn(d_model, generator=g)).to(dtype)
+    w["backbone.norm_f.bias"] = (0.05 * torch.randn(d_model, generator=g)).to(dtype)
+    for k in range(n_codebooks):
+        w[f"embeddings.{k}.weight"] = torch.randn(emb_vocab, d_model, generator=g).to(dtype)
+    w["fused_heads.weight"] = _uniform(g, (n_codebooks * head_vocab, d_model), heads_scale / math.sqrt(d_model), dtype)
+    return w

@@ -249,7 +249,43 @@ def golden_dac():
     np.savez_compressed(os.path.join(HERE, "dac_decode.npz"), codes=codes.numpy(), wav=wav.numpy())
 
 
+# ---------------------------------------------------------------- prefix conditioner (tensor conditioners)
+COND_CFG = dict(projection="linear", conditioners=[
+    dict(type="PassthroughConditioner", name="speaker", cond_dim=128, uncond_type="learned", projection="linear"),
+    dict(type="FourierConditioner", name="emotion", input_dim=8, uncond_type="learned"),
+    dict(type="FourierConditioner", name="fmax", min_val=0, max_val=24000, uncond_type="learned"),
+    dict(type="FourierConditioner", name="pitch_std", min_val=0, max_val=400, uncond_type="learned"),
+    dict(type="IntegerConditioner", name="language_id", min_val=-1, max_val=126, uncond_type="learned")])
+
+
+def golden_conditioner():
+    from zonos.conditioning import PrefixConditioner as RefPC
+    from zonos.config import PrefixConditionerConfig as RefCfg
+    from zonos.utilities.conditioning_cache import prepare_conditioning_with_cache as ref_prepare
+    from zonos_b200.conditioning import PrefixConditioner, prepare_conditioning_with_cache
+    from zonos_b200.config import PrefixConditionerConfig
+    torch.manual_seed(21)
+    ref = RefPC(RefCfg(**COND_CFG), 64).eval()
+    with torch.no_grad():
+        for c in ref.conditioners:
+            c.uncond_vector.normal_()
+    g = torch.Generator().manual_seed(22)
+    cond = {"speaker": torch.randn(1, 1, 128, generator=g), "emotion": torch.rand(1, 1, 8, generator=g),
+            "fmax": torch.tensor([[[22050.0]]]), "pitch_std": torch.tensor([[[45.0]]]), "language_id": torch.tensor([[[24]]])}
+    uncond = {"emotion": cond["emotion"]}
+    out = ref_prepare(ref, cond, uncond, cfg_scale=2.0)
+    mine = PrefixConditioner(PrefixConditionerConfig(**COND_CFG), 64).eval()
+    mine.load_state_dict(ref.state_dict())
+    got = prepare_conditioning_with_cache(mine, cond, uncond, cfg_scale=2.0)
+    assert torch.equal(got, out), (got - out).abs().max()
+    np.savez_compressed(os.path.join(HERE, "prefix_conditioner.npz"), out=out.numpy(),
+                        **{"sd__" + k: v.numpy() for k, v in ref.state_dict().items()},
+                        **{"in__" + k: v.numpy() for k, v in cond.items()})
+    print("prefix conditioner:", tuple(out.shape))
+
+
 if __name__ == "__main__":
+    golden_conditioner()
     golden_codebook()
     golden_sampler()
     golden_generate()

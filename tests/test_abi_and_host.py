@@ -92,3 +92,33 @@ def test_finalize_matches_oracle():
             delayed[:, :, T - 8:] = 1024
         offset = T + 9 - (trial % 5)
         assert torch.equal(m._finalize(delayed.clone(), offset), finalize_codes(delayed.clone(), offset))
+
+
+def test_prefix_conditioner_matches_reference_golden():
+    """Tensor conditioners + projection + LayerNorm + CFG concatenation vs the fixture recorded from the reference."""
+    from helpers import load_golden
+    from zonos_b200.conditioning import PrefixConditioner, make_cond_dict, prepare_conditioning_with_cache, tokenize_phonemes
+    from zonos_b200.config import PrefixConditionerConfig
+    cfg = dict(projection="linear", conditioners=[
+        dict(type="PassthroughConditioner", name="speaker", cond_dim=128, uncond_type="learned", projection="linear"),
+        dict(type="FourierConditioner", name="emotion", input_dim=8, uncond_type="learned"),
+        dict(type="FourierConditioner", name="fmax", min_val=0, max_val=24000, uncond_type="learned"),
+        dict(type="FourierConditioner", name="pitch_std", min_val=0, max_val=400, uncond_type="learned"),
+        dict(type="IntegerConditioner", name="language_id", min_val=-1, max_val=126, uncond_type="learned")])
+    g = load_golden("prefix_conditioner.npz")
+    pc = PrefixConditioner(PrefixConditionerConfig(**cfg), 64).eval()
+    pc.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd__")})
+    cond = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in__")}
+    cache = {}
+    with torch.no_grad():
+        out = prepare_conditioning_with_cache(pc, cond, {"emotion": cond["emotion"]}, use_cache=True, cfg_scale=2.0, cache=cache)
+        again = prepare_conditioning_with_cache(pc, cond, {"emotion": cond["emotion"]}, use_cache=True, cfg_scale=2.0, cache=cache)
+    assert out.shape == (2, 5, 64) and np.array_equal(out.numpy(), g["out"])
+    assert again is out and len(cache) == 1
+    with pytest.raises(ValueError):
+        PrefixConditioner(PrefixConditionerConfig(projection="none", conditioners=[dict(type="PassthroughConditioner", name="x")]), 8)({})
+    ids, lens = tokenize_phonemes(["həlˈoʊ", "a"])
+    assert ids.shape == (2, 8) and ids[1, :5].tolist() == [0] * 5 and ids[0, 0] == 2 and ids[0, -1] == 3 and lens == [8, 3]
+    d = make_cond_dict(text="hi", speaker=torch.zeros(1, 1, 128), device="cpu")
+    assert set(d) == {"espeak", "speaker", "emotion", "fmax", "pitch_std", "speaking_rate", "language_id", "ctc_loss", "speaker_noised"}
+    assert d["language_id"].item() == 24 and abs(float(d["emotion"].sum()) - 1.0) < 1e-6

@@ -282,6 +282,22 @@ def test_dac_decode_properties():
     assert ae.decode(codes[:, :, :0]).shape == (2, 1, 0)
 
 
+def test_generate_stream_equals_generate_plus_decode():
+    """Streaming (chunked DAC decode while the loop runs) emits exactly the codes of generate() and, sample for sample,
+    the waveform of a full decode (the hold-back covers the decoder's receptive field)."""
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    model = build_b200_model(TINY_DIMS, w, DEV, dac_weights=make_dac_weights(seed=1))
+    cond = make_conditioning(2, 9, TINY_DIMS["d_model"]).to(DEV)
+    full = model.generate(cond, max_new_tokens=150, seed=3)
+    wav_full = model.autoencoder.decode(full)
+    chunks = list(model.generate_stream(cond, max_new_tokens=150, seed=3, chunk_frames=43))
+    assert len(chunks) >= 3
+    codes = torch.cat([c for _, c in chunks], dim=-1)
+    wav = torch.cat([w_ for w_, _ in chunks], dim=-1)
+    assert torch.equal(codes, full)
+    assert wav.shape == wav_full.shape and torch.equal(wav, wav_full)
+
+
 # ------------------------------------------------------------------------------ hybrid (Mamba2) --
 def _hybrid_model(device):
     from oracle.hybrid import HybridDims, HybridOracle

@@ -261,6 +261,88 @@ class Zonos(nn.Module):
             trace.update(delayed=delayed.clone(), offset=offset, steps=int(prog.steps), logits=logits_trace, seed=seed)
         return self._finalize(delayed, offset)
 
+
+    # ---------------------------------------------------------------- streaming -----------
+    @torch.inference_mode()
+    def generate_stream(self, prefix_conditioning: torch.Tensor, audio_prefix_codes: torch.Tensor | None = None,
+                        max_new_tokens: int = 86 * 30, cfg_scale: float = 2.0, batch_size: int = 1,
+                        sampling_params: dict = dict(min_p=0.1), *, chunk_frames: int = 43, holdback_frames: int = 32,
+                        seed: int | None = None):
+        """Generator of (wav fp32 [B,1,512*n], codes int64 [B,9,n]) chunks: the same loop as `generate`, but finished frames
+        are DAC-decoded while the loop keeps running (the reference can only decode after `generate` returns).
+
+        A frame is final once the loop front is `holdback_frames` past it: 32 >= the decoder's receptive field (so every
+        emitted sample equals the one a full decode produces) and >= the span the reference's EOS-boundary scan can still
+        cut (model.py:513-528 looks at most 9 + 16 frames behind the stop).  Time to first audio = prefill +
+        (chunk_frames + holdback_frames + 9) decode steps + one chunk decode."""
+        assert cfg_scale != 1, "TODO: add support for cfg_scale=1"
+        device = self.device
+        Q, B = self.num_codebooks, batch_size
+        P = 0 if audio_prefix_codes is None else audio_prefix_codes.shape[2]
+        cond = prefix_conditioning.to(device, torch.bfloat16).contiguous()
+        assert cond.shape[0] == 2 * B
+        Lc = cond.shape[1]
+        params = self.setup_cache(batch_size=2 * B, max_seqlen=Lc + P + max_new_tokens + Q)
+        codes = torch.full((B, Q, P + max_new_tokens), -1, dtype=torch.int64, device=device)
+        if audio_prefix_codes is not None:
+            codes[..., :P] = audio_prefix_codes.to(device)
+        delayed = apply_delay_pattern(codes, self.masked_token_id).contiguous()
+        T_delayed = delayed.shape[2]
+        if seed is None:
+            seed = int(torch.randint(0, 2**62, (1,)).item())
+        desc = _lib.zb_gen_desc()
+        desc.B, desc.Q, desc.T_delayed, desc.prefix_audio_len, desc.cond_len, desc.max_new_tokens = B, Q, T_delayed, P, Lc, max_new_tokens
+        desc.delayed, desc.prefix_conditioning, desc.cfg_scale = delayed.data_ptr(), cond.data_ptr(), float(cfg_scale)
+        desc.sampling = sampling_struct(**sampling_params)
+        desc.seed = seed
+        ctx = self._ctx()
+        lib = ctx.lib
+        cache = self.backbone._cache.desc(params.lengths_per_sample)
+        stream = _lib.stream_ptr(device)
+        gen = C.c_void_p()
+        prog = _lib.zb_gen_progress()
+        halo = 16                                                   # frames of decoder context on each side of a chunk
+        emitted = P                                                 # frames [0, emitted) are done (the prefix is not re-emitted)
+
+        def emit(lo: int, hi: int, last: bool):
+            ctx_lo = max(0, lo - halo)
+            ctx_hi = hi if last else hi + halo
+            part = revert_delay_pattern(delayed[..., :ctx_hi + Q + 1])[..., ctx_lo:ctx_hi]
+            part = torch.where(part > 1024, torch.full_like(part, 512), part)
+            part = torch.where(part == 1024, torch.zeros_like(part), part).clamp(0, 1023)
+            wav = self.autoencoder.decode(part)
+            return wav[..., 512 * (lo - ctx_lo):512 * (hi - ctx_lo)], part[..., lo - ctx_lo:hi - ctx_lo]
+
+        with ctx.lock:
+            ctx.check(lib.zb_generate_begin(ctx.handle, self._native_model(), C.byref(cache), C.byref(desc), C.byref(gen), stream))
+            try:
+                max_steps = T_delayed - (P + 1)
+                enq = 0
+                while True:
+                    # run until the next chunk is final: front (= offset - Q complete frames) >= emitted + chunk + holdback
+                    need_front = emitted + chunk_frames + holdback_frames
+                    need_steps = min(max_steps, need_front + Q - (P + 1))
+                    if need_steps > enq:
+                        ctx.check(lib.zb_generate_steps(gen, need_steps - enq, stream))
+                        enq = need_steps
+                    ctx.check(lib.zb_generate_poll(gen, C.byref(prog), stream))
+                    front = int(prog.offset) - Q
+                    if prog.done or enq >= max_steps:
+                        break
+                    hi = min(front - holdback_frames, emitted + chunk_frames)
+                    if hi > emitted:
+                        yield emit(emitted, hi, last=False)
+                        emitted = hi
+                final = self._finalize(delayed, int(prog.offset))
+                if final.shape[-1] > emitted - 0:
+                    valid = final.shape[-1]
+                    if valid > emitted:
+                        ctx_lo = max(0, emitted - halo)
+                        wav = self.autoencoder.decode(final[..., ctx_lo:valid])
+                        yield wav[..., 512 * (emitted - ctx_lo):], final[..., emitted:valid]
+            finally:
+                lib.zb_generate_end(gen)
+
     def _finalize(self, delayed: torch.Tensor, offset: int) -> torch.Tensor:
         """zonos/model.py:511-539: revert the delay pattern, batch-global EOS-boundary scan over the last <=50
         positions, sanitise (mask -> 512, EOS -> 0), slice, clamp."""

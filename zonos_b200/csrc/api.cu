@@ -35,6 +35,12 @@ zb_status zb_scratch_reserve(zb_ctx* ctx, size_t bytes) {
 zb_status zb_dac_scratch_reserve(zb_ctx* ctx, size_t bytes) {
   return arena_reserve(ctx, &ctx->dac_scratch, &ctx->dac_scratch_bytes, bytes);
 }
+zb_status zb_tc_workspace_reserve(zb_ctx* ctx, size_t bytes) {
+  // fixed 64 MB, allocated once: [0, 48 MB) split-K partials (at most 296 tiles x 128 x 256 fp32 = 39 MB), [48, 64 MB) row staging;
+  // it never moves, so CUDA graphs may bake its address
+  if (bytes > ((size_t)48 << 20)) return zb_fail(ctx, ZB_ERR_INVALID, "split-K workspace request of %zu bytes exceeds 48 MB", bytes);
+  return arena_reserve(ctx, &ctx->tc_ws, &ctx->tc_ws_bytes, (size_t)64 << 20);
+}
 
 extern "C" {
 
@@ -77,6 +83,7 @@ zb_status zb_ctx_destroy(zb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->dac_scratch) cudaFree(ctx->dac_scratch);
+  if (ctx->tc_ws) cudaFree(ctx->tc_ws);
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
   delete ctx;

@@ -29,6 +29,8 @@ struct zb_ctx {
   int scratch_pins = 0;
   void* dac_scratch = nullptr;
   size_t dac_scratch_bytes = 0;
+  void* tc_ws = nullptr;          // split-K partial sums of the tcgen05 GEMM
+  size_t tc_ws_bytes = 0;
   int32_t* counters = nullptr;  // zeroed int32 words for last-CTA-done patterns
   cudaStream_t capture_stream = nullptr;   // graph capture happens here (the caller's stream may be the legacy one)
 };
@@ -61,6 +63,7 @@ zb_status zb_fail(zb_ctx* ctx, zb_status code, const char* fmt, ...);
 
 zb_status zb_scratch_reserve(zb_ctx* ctx, size_t bytes);
 zb_status zb_dac_scratch_reserve(zb_ctx* ctx, size_t bytes);
+zb_status zb_tc_workspace_reserve(zb_ctx* ctx, size_t bytes);
 
 // ------------------------------------------------------------------------------------------
 // device helpers

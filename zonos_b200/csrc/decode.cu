@@ -1685,6 +1685,25 @@ zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden
     ZB_REQUIRE(ctx, R % 2 == 0, "CFG needs an even number of rows");
     a.B = R / 2;
   } else a.B = R;
+  if (R > 4 && R <= 256 && d.d_model % 64 == 0) {   // (runs even when the device loop is done: outputs are then unused)
+    // dense path: (final norm ->) tcgen05 GEMM with the fp32 CFG-mix epilogue
+    if (zb_status st = zb_tc_workspace_reserve(ctx, 0)) return st;
+    const bf16* src = hidden;
+    long long ld = row_stride;
+    if (apply_norm) {
+      bf16* xn = (bf16*)((char*)ctx->tc_ws + ((size_t)48 << 20));
+      NormArgs na;
+      na.x = hidden; na.ldx = row_stride; na.y = xn; na.ldy = d.d_model; na.w = (const bf16*)d.norm_f_w; na.b = (const bf16*)d.norm_f_b;
+      na.D = d.d_model; na.eps = d.norm_eps; na.kind = d.norm_kind;
+      ZB_CUDA(ctx, zb_launch_pdl(norm_kernel, dim3(R), dim3(256), 0, stream, na));
+      ctx->launches++;
+      src = xn; ld = d.d_model;
+    }
+    zb_gemm_tc g;
+    g.W = (const bf16*)d.heads; g.x = src; g.ldx = ld; g.M = R; g.N = a.N; g.K = d.d_model; g.epi = 4;
+    g.B = a.B; g.cfg_scale = cfg_scale; g.logits = logits; g.QV = a.N;
+    return zb_launch_gemm_tc(ctx, g, stream);
+  }
   if (apply_norm) return launch_gemv<PRO_NORM, EPI_HEADS>(ctx, a, stream);
   return launch_gemv<PRO_NONE, EPI_HEADS>(ctx, a, stream);
 }

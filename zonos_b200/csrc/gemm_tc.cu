@@ -8,6 +8,8 @@
 //   warps 0-3: epilogue: tcgen05.ld 32 lanes x 16 columns -> registers -> fused epilogue (same rounding points as
 //              the GEMV path: bf16 Linear output, then residual / SiLU gate / RoPE + paged KV append / fp32 CFG mix)
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA).
+#include <stdlib.h>
+
 #include "tc.cuh"
 
 namespace {
@@ -29,6 +31,9 @@ struct TcArgs {
   const float* rope; const int32_t* lengths; const int32_t* page_table; bf16* kv_layer; bf16* q_out;
   // HEADS
   int B; float cfg_scale; float* logits; int QV;
+  // split-K: grid.z CTAs share one output tile; fp32 partials meet in `ws`, the last CTA to arrive reduces them in
+  // split order (deterministic) and runs the epilogue
+  int ksplit; float* ws; int32_t* counters;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcArgs a) {
@@ -49,7 +54,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   int row_lo, row_hi;
   if (a.epi == TEPI_SILU) { row_lo = n_tile * 64; row_hi = a.F + n_tile * 64; }
   else { row_lo = n_tile * TC_BM; row_hi = row_lo + 64; }
-  const int nk = a.K / TC_BK;
+  const int nk_total = a.K / TC_BK;
+  const int nk_per = (nk_total + a.ksplit - 1) / a.ksplit;
+  const int kb0 = blockIdx.z * nk_per;
+  const int nk = max(0, min(nk_total, kb0 + nk_per) - kb0);          // k-blocks of this split
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -77,9 +85,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         unsigned char* sa = base + (size_t)s * stage_bytes;
         unsigned char* sb = sa + a_bytes;
         mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
-        tma_load_2d(sa, &a.map_w, kb * TC_BK, row_lo, &full_bar[s]);
-        tma_load_2d(sa + a_bytes / 2, &a.map_w, kb * TC_BK, row_hi, &full_bar[s]);
-        tma_load_2d(sb, &a.map_x, kb * TC_BK, m0, &full_bar[s]);
+        tma_load_2d(sa, &a.map_w, (kb0 + kb) * TC_BK, row_lo, &full_bar[s]);
+        tma_load_2d(sa + a_bytes / 2, &a.map_w, (kb0 + kb) * TC_BK, row_hi, &full_bar[s]);
+        tma_load_2d(sb, &a.map_x, (kb0 + kb) * TC_BK, m0, &full_bar[s]);
       }
     }
   } else if (warp == 5) {
@@ -104,6 +112,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const int lr = warp * 32 + lane;                                   // row inside the 128-row tile
+    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    float* ws_tile = a.ws + (size_t)tile_id * a.ksplit * TC_BM * BN;   // [ksplit][128][BN]
+    if (a.ksplit > 1) {
+      __shared__ int s_last_tc;
+      float* mine = ws_tile + ((size_t)blockIdx.z * TC_BM + lr) * BN;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(mine + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        int prev;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(prev) : "l"(a.counters + tile_id) : "memory");
+        s_last_tc = (prev == a.ksplit - 1);
+        if (s_last_tc) a.counters[tile_id] = 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!s_last_tc) { tc_fence_before(); goto tc_done; }
+    }
+    // accumulator chunk: straight from TMEM, or (split-K) the sum of all partials in split order
+    auto load_chunk = [&](int c0, float (&v)[16]) {
+      if (a.ksplit == 1) { tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v); return; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      for (int sp = 0; sp < a.ksplit; ++sp) {
+        const float* src = ws_tile + ((size_t)sp * TC_BM + lr) * BN + c0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + j));
+          v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+        }
+      }
+    };
     const int n = (lr < 64) ? row_lo + lr : row_hi + (lr - 64);        // weight row == output feature
     const bool n_ok = n < a.N;
     float* xchg = reinterpret_cast<float*>(base);                      // SILU: gate values [64][BN] (ring is idle now)
@@ -112,7 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (warp >= 2) {
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float v[16];
-          tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+          load_chunk(c0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j) xchg[(size_t)(lr - 64) * BN + c0 + j] = rbf(v[j]);
         }
@@ -121,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (warp < 2) {
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float v[16];
-          tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+          load_chunk(c0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int m = m0 + c0 + j;
@@ -136,7 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     } else {
       for (int c0 = 0; c0 < BN; c0 += 16) {
         float v[16];
-        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        load_chunk(c0, v);
         if (a.epi == TEPI_HEADS && a.cfg_scale != 1.0f) {
           // columns [0,B) are cond rows, [B,2B) uncond rows (single m tile): park the bf16-rounded row in shared memory
           // (the ring is idle now) and mix in a second pass, so no unaligned TMEM column reads are needed
@@ -144,38 +187,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           for (int j = 0; j < 16; ++j) xchg[(size_t)lr * BN + c0 + j] = rbf(v[j]);
           continue;
         }
+        if (a.epi == TEPI_QKV) {
+          // RoPE pairs (2i, 2i+1) sit in adjacent lanes (interleaved convention, _torch.py:57-68).  Positions, pages and
+          // cos/sin of the 16 columns are fetched up front (independent loads) instead of one dependent chain per element.
+          const int qn = a.Hq * a.hd, kn = a.Hkv * a.hd;
+          const bool rot = n < qn + kn;
+          int pos[16];
+          float2 cs[16];
+          int page[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int m = m0 + c0 + j;
-          const float val = v[j];
-          if (a.epi == TEPI_QKV) {
-            // RoPE pairs (2i, 2i+1) sit in adjacent lanes (interleaved convention, _torch.py:57-68)
-            const float other = __shfl_xor_sync(0xffffffffu, rbf(val), 1);
+          for (int j = 0; j < 16; ++j) {
+            const int m = min(m0 + c0 + j, a.M - 1);
+            pos[j] = a.lengths[m / a.T] + m % a.T;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = min(m0 + c0 + j, a.M - 1);
+            cs[j] = rot && n_ok ? *reinterpret_cast<const float2*>(a.rope + ((size_t)min(pos[j], a.rope_len - 1) * (a.hd / 2) + (n % a.hd) / 2) * 2)
+                                : make_float2(1.f, 0.f);
+            page[j] = (n >= qn && n_ok) ? a.page_table[(size_t)(m / a.T) * a.max_pages + pos[j] / ZB_PAGE_TOKENS] : 0;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + c0 + j;
+            float o = rbf(v[j]);
+            const float other = __shfl_xor_sync(0xffffffffu, o, 1);
             if (m < a.M && n_ok) {
-              const int r = m / a.T, t = m % a.T;
-              const int pos = a.lengths[r] + t;
-              const int qn = a.Hq * a.hd, kn = a.Hkv * a.hd;
-              float o = rbf(val);
-              if (n < qn + kn) {
-                const int i = (n % a.hd) / 2;
-                const float2 cs = *reinterpret_cast<const float2*>(a.rope + ((size_t)min(pos, a.rope_len - 1) * (a.hd / 2) + i) * 2);
-                o = (n & 1) ? __fadd_rn(__fmul_rn(o, cs.x), __fmul_rn(other, cs.y))      // x1*c + x0*s
-                            : __fsub_rn(__fmul_rn(o, cs.x), __fmul_rn(other, cs.y));     // x0*c - x1*s
-              }
+              if (rot) o = (n & 1) ? __fadd_rn(__fmul_rn(o, cs[j].x), __fmul_rn(other, cs[j].y))      // x1*c + x0*s
+                                   : __fsub_rn(__fmul_rn(o, cs[j].x), __fmul_rn(other, cs[j].y));     // x0*c - x1*s
               if (n < qn) {
                 a.q_out[(size_t)m * qn + n] = f2bf(o);
               } else {
                 const int kvsel = n < qn + kn ? 0 : 1;
                 const int ci = n - qn - kvsel * kn;
-                const int page = a.page_table[(size_t)r * a.max_pages + pos / ZB_PAGE_TOKENS];
-                bf16* pb = a.kv_layer + ((size_t)page * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
-                pb[((size_t)(ci / a.hd) * ZB_PAGE_TOKENS + pos % ZB_PAGE_TOKENS) * a.hd + (ci % a.hd)] = f2bf(o);
+                bf16* pb = a.kv_layer + ((size_t)page[j] * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
+                pb[((size_t)(ci / a.hd) * ZB_PAGE_TOKENS + pos[j] % ZB_PAGE_TOKENS) * a.hd + (ci % a.hd)] = f2bf(o);
               }
             }
-          } else if (m < a.M && n_ok) {
-            if (a.epi == TEPI_STORE) a.y[(size_t)m * a.ldy + n] = f2bf(val);
-            else if (a.epi == TEPI_RESID) a.y[(size_t)m * a.ldy + n] = f2bf(bf2f(a.resid[(size_t)m * a.ldr + n]) + rbf(val));
-            else if (a.epi == TEPI_HEADS) a.logits[(size_t)m * a.QV + n] = rbf(val);
+          }
+          continue;
+        }
+        if (a.epi == TEPI_RESID) {
+          float rv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {                     // 16 independent loads in flight, then 16 stores
+            const int m = m0 + c0 + j;
+            rv[j] = (m < a.M && n_ok) ? __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(a.resid + (size_t)m * a.ldr + n)) << 16) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + c0 + j;
+            if (m < a.M && n_ok) a.y[(size_t)m * a.ldy + n] = f2bf(rv[j] + rbf(v[j]));
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int m = m0 + c0 + j;
+          if (m < a.M && n_ok) {
+            if (a.epi == TEPI_STORE) a.y[(size_t)m * a.ldy + n] = f2bf(v[j]);
+            else if (a.epi == TEPI_HEADS) a.logits[(size_t)m * a.QV + n] = rbf(v[j]);
           }
         }
       }
@@ -188,6 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
     tc_fence_before();
   }
+tc_done:
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
@@ -248,7 +320,25 @@ zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t strea
     attr = smem;
   }
   const int ntiles = (g.epi == TEPI_SILU) ? (g.F + 63) / 64 : (g.N + TC_BM - 1) / TC_BM;
-  ZB_CUDA(ctx, zb_launch_pdl(gemm_tc_kernel, dim3(ntiles, mtiles), dim3(TC_THREADS), smem, stream, a));
+  // split-K for the bandwidth-bound small-M regime: enough CTAs to pull weights with every SM
+  int ksplit = 1;
+  static const int splitk_on = getenv("ZB_TC_SPLITK") ? atoi(getenv("ZB_TC_SPLITK")) : 0;   // measured slower on B200 (B=64 decode: 1.75 s vs 1.52 s per pass): off by default
+  if (splitk_on && mtiles == 1 && ntiles < ctx->num_sms) {
+    ksplit = (ctx->num_sms + ntiles - 1) / ntiles;
+    const int nkb = g.K / TC_BK;
+    if (ksplit > nkb / 4) ksplit = nkb / 4;              // at least 4 k-blocks (256 k) per split
+    if (ksplit > 16) ksplit = 16;
+    if (ksplit < 1) ksplit = 1;
+  }
+  a.ksplit = ksplit;
+  if (ksplit > 1) {
+    const size_t ws_bytes = (size_t)ntiles * ksplit * TC_BM * BN * sizeof(float);
+    if (zb_status st = zb_tc_workspace_reserve(ctx, ws_bytes)) return st;
+    ZB_REQUIRE(ctx, (size_t)ntiles + 65536 <= ZB_NUM_COUNTERS, "gemm_tc: too many tiles for the split-K counters");
+    a.ws = (float*)ctx->tc_ws;
+    a.counters = ctx->counters + 65536 * 8;              // disjoint from the attention-merge counters
+  }
+  ZB_CUDA(ctx, zb_launch_pdl(gemm_tc_kernel, dim3(ntiles, mtiles, ksplit), dim3(TC_THREADS), smem, stream, a));
   ctx->launches++;
   return ZB_OK;
 }

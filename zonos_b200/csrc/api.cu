@@ -189,7 +189,8 @@ struct zb_gen {
   float* logits = nullptr;          // [B,Q,V]
   bf16* xdec = nullptr;             // [2B, D] residual stream of one decode step
   void* mega_layers = nullptr;      // device array of per-layer pointers for the persistent decode kernel
-  unsigned* mega_bar = nullptr;     // grid barrier words
+  unsigned* mega_bar = nullptr;     // sync words of the persistent kernel ([1] = epoch of the tagged arena)
+  uint32_t* mega_arena = nullptr;   // tagged activation words exchanged between its CTAs
   bool mega = false;
   cudaGraphExec_t graph = nullptr;
   int64_t launches_per_step = 0;
@@ -214,7 +215,7 @@ zb_status enqueue_step(zb_gen* g, cudaStream_t s) {
   E.B = B; E.T = 1; E.repeat = 2; E.out = g->xdec; E.out_rs = md.d_model; E.loop = g->st; E.T_delayed = g->d.T_delayed;
   if (g->mega) {
     // one cooperative launch: embed + all layers + heads
-    if (zb_status st = zb_launch_decode_step(ctx, g->model, &g->cache, g->mega_layers, g->mega_bar, g->xdec, R, g->max_kv, g->d.cfg_scale, g->logits,
+    if (zb_status st = zb_launch_decode_step(ctx, g->model, &g->cache, g->mega_layers, g->mega_bar, g->mega_arena, R, g->max_kv, g->d.cfg_scale, g->logits,
                                              g->d.delayed, g->d.T_delayed, g->st, s)) return st;
   } else {
     if (zb_status st = zb_launch_embed(ctx, E, s)) return st;
@@ -225,7 +226,7 @@ zb_status enqueue_step(zb_gen* g, cudaStream_t s) {
   L.logits = g->logits; L.B = B; L.Q = g->d.Q; L.V = md.head_vocab; L.sp = g->d.sampling; L.apply_bias = 1; L.seed = g->d.seed;
   L.st = g->st; L.delayed = g->d.delayed; L.T = g->d.T_delayed; L.ctx_len = g->d.max_new_tokens < 100 ? g->d.max_new_tokens : 100;
   L.lengths = g->cache.lengths; L.q_stream = g->d.q_stream; L.q_calls = g->d.q_calls; L.logits_trace = g->d.logits_trace;
-  L.trace_calls = g->d.trace_calls; L.first = 0; L.mirror = g->st_host_dev; L.reset_word = g->mega_bar;
+  L.trace_calls = g->d.trace_calls; L.first = 0; L.mirror = g->st_host_dev; L.reset_word = nullptr;
   return zb_launch_sample(ctx, L, s);
 }
 }  // namespace
@@ -272,6 +273,8 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
     G_CUDA(cudaStreamSynchronize(s));                   // hb is a stack-scoped staging buffer
     G_CUDA(cudaMalloc(&g->mega_bar, 2 * sizeof(unsigned)));
     G_CUDA(cudaMemsetAsync(g->mega_bar, 0, 2 * sizeof(unsigned), s));
+    G_CUDA(cudaMalloc(&g->mega_arena, zb_mega_arena_bytes(model, R)));
+    G_CUDA(cudaMemsetAsync(g->mega_arena, 0, zb_mega_arena_bytes(model, R), s));   // tag 0 = never written
   }
   const int offset0 = P + 1;
   g->max_steps = desc->T_delayed - offset0;               // model.py:440
@@ -374,6 +377,7 @@ zb_status zb_generate_end(zb_gen* gen) {
   if (gen->xdec) cudaFree(gen->xdec);
   if (gen->mega_layers) cudaFree(gen->mega_layers);
   if (gen->mega_bar) cudaFree(gen->mega_bar);
+  if (gen->mega_arena) cudaFree(gen->mega_arena);
   delete gen;
   return ZB_OK;
 }

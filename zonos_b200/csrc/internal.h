@@ -64,9 +64,10 @@ size_t zb_backbone_scratch_bytes(const zb_model* model, int R, int T, int max_kv
 // persistent single-launch decode step (decode.cu)
 bool zb_mega_supported(const zb_model* model, int R);
 size_t zb_mega_layers_bytes(const zb_model* model);
+size_t zb_mega_arena_bytes(const zb_model* model, int R);     // tagged activation words of one generate session (zeroed by the caller)
 zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf);
-zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const void* mega_layers_dev, unsigned* bar,
-                                bf16* x, int R, int max_kv_len, float cfg_scale, float* logits, const int64_t* delayed, int T_delayed,
+zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const void* mega_layers_dev, unsigned* sync,
+                                uint32_t* arena, int R, int max_kv_len, float cfg_scale, float* logits, const int64_t* delayed, int T_delayed,
                                 const zb_loop_state* loop, cudaStream_t stream);
 
 // ---- tcgen05 GEMM (gemm_tc.cu): Y[M,N] = X[M,K] W[N,K]^T with fused epilogue ----

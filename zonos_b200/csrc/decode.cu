@@ -1814,8 +1814,9 @@ zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cach
   const zb_model_desc& d = model->d;
   const size_t page_elems = (size_t)2 * d.n_heads_kv * ZB_PAGE_TOKENS * d.head_dim;
   MegaLayer* out = (MegaLayer*)host_buf;
+  static const int share = env_int("ZB_DEBUG_SHARE_LAYERS", 0);   // debug: every layer streams layer 0's weights (L2-resident experiment)
   for (int li = 0; li < d.n_layer; ++li) {
-    const zb_layer& L = model->layers[li];
+    const zb_layer& L = model->layers[share ? 0 : li];
     ZB_REQUIRE(ctx, L.kind == ZB_LAYER_ATTENTION, "persistent decode: layer %d is not an attention layer", li);
     out[li].norm_w = (const bf16*)L.norm_w; out[li].norm_b = (const bf16*)L.norm_b; out[li].in_proj = (const bf16*)L.in_proj;
     out[li].out_proj = (const bf16*)L.out_proj; out[li].norm2_w = (const bf16*)L.norm2_w; out[li].norm2_b = (const bf16*)L.norm2_b;

@@ -718,11 +718,11 @@ struct MegaArgs {
   float* attn_part; int32_t* attn_counters; int nsplit; float scale;
   const zb_loop_state* loop;
   unsigned* sync;         // [1] = epoch: number of live steps this session's tagged buffers have seen
-  int ring_stages, part_bytes;
+  int ring_stages, part_bytes, evict_first;
   unsigned long long* timeline;   // debug: globaltimer stamps of CTA 0 (2 per phase: inputs ready, work done)
 };
 
-constexpr int kMegaStageBytes = 32 * 1024;
+constexpr int kMegaStageBytes = 32 * 1024, kMegaAttnBytes = 40 * 1024;
 
 // ---- tagged activation words -----------------------------------------------------------------------------------
 // The phases of a step depend on each other all-to-all (every CTA needs the whole activation vector the previous
@@ -797,11 +797,16 @@ __device__ __forceinline__ void mega_produce(const GemvArgs& a, unsigned char* r
     __syncwarp();
     unsigned char* dst = ring + (size_t)slot * kMegaStageBytes;
     if (!kPairs && r0 + RPS <= nrows) {
-      if (lane == 0) bulk_g2s(dst, a.W + (size_t)(u_begin + r0) * K, (uint32_t)kMegaStageBytes, &full_bar[slot], pol);
+      if (lane == 0) {
+        if (pol) bulk_g2s(dst, a.W + (size_t)(u_begin + r0) * K, (uint32_t)kMegaStageBytes, &full_bar[slot], pol);
+        else bulk_g2s_nohint(dst, a.W + (size_t)(u_begin + r0) * K, (uint32_t)kMegaStageBytes, &full_bar[slot]);
+      }
     } else {
       for (int q = lane; q < RPS; q += 32) {
         const int lr = min(r0 + q, nrows - 1);
-        bulk_g2s(dst + (size_t)q * row_bytes, a.W + (size_t)row_of_local<EPI>(a, u_begin, lr) * K, row_bytes, &full_bar[slot], pol);
+        const bf16* src = a.W + (size_t)row_of_local<EPI>(a, u_begin, lr) * K;
+        if (pol) bulk_g2s(dst + (size_t)q * row_bytes, src, row_bytes, &full_bar[slot], pol);
+        else bulk_g2s_nohint(dst + (size_t)q * row_bytes, src, row_bytes, &full_bar[slot]);
       }
     }
   }
@@ -812,7 +817,7 @@ template <int R, int NC, int RW, int PRO, int EPI>
 __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* ring, float* part, uint64_t* full_bar, uint64_t* empty_bar,
                                              float (*red)[kW3][4], int S, int& gst, bool release, int warp, int lane,
                                              const uint32_t* xt, uint32_t tag_in, uint32_t* yt, uint32_t tag_out, const uint32_t* rt, uint32_t* qt,
-                                             uint32_t* kvt, unsigned long long* stamp) {
+                                             uint32_t* kvt, unsigned long long* stamp, int norm_pending = 0) {
   constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
   constexpr int Kc = NC * 256;
   const int K = a.K, row_bytes = K * 2;
@@ -823,16 +828,6 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   const int nstage = (nrows + RPS - 1) / RPS;
   const int ks = warp % KS, rg = warp / KS;
   const size_t koff = (size_t)ks * Kc;
-  uint4 nwr[NC], nbr[NC];                                      // norm parameters: in flight together with the activations
-  if (PRO == PRO_NORM) {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const size_t k = koff + c * 256 + lane * 8;
-      nwr[c] = *reinterpret_cast<const uint4*>(a.nw + k);
-      nbr[c] = a.nb ? *reinterpret_cast<const uint4*>(a.nb + k) : make_uint4(0, 0, 0, 0);
-    }
-  }
-
   // activations: spin on the operand loads themselves until every word carries the producing phase's tag
   float xf[R][NC * 8];
   for (unsigned spins = 0;; ++spins) {
@@ -862,6 +857,10 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
       qacc = warp_sum(qacc);
       if (rg == 0 && lane == 0) { red[0][ks][i] = sacc; red[1][ks][i] = qacc; }
     }
+    // the norm parameters sit in shared memory (copied there a layer ahead: a global load issued here would queue
+    // behind the saturated weight stream for microseconds); this thread's copies are complete after the wait, all
+    // threads' after the barrier
+    if (norm_pending == 0) asm volatile("cp.async.wait_group 0;" ::: "memory"); else asm volatile("cp.async.wait_group 1;" ::: "memory");
     asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
 #pragma unroll
     for (int i = 0; i < R; ++i) {
@@ -874,7 +873,10 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const uint32_t gv[4] = {nwr[c].x, nwr[c].y, nwr[c].z, nwr[c].w}, bv[4] = {nbr[c].x, nbr[c].y, nbr[c].z, nbr[c].w};
+      const size_t kk = koff + c * 256 + lane * 8;
+      const uint4 nwv = *reinterpret_cast<const uint4*>(a.nw + kk);
+      const uint4 nbv = a.nb ? *reinterpret_cast<const uint4*>(a.nb + kk) : make_uint4(0, 0, 0, 0);
+      const uint32_t gv[4] = {nwv.x, nwv.y, nwv.z, nwv.w}, bv[4] = {nbv.x, nbv.y, nbv.z, nbv.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float g0 = bf16lo(gv[j]), g1 = bf16hi(gv[j]), b0 = bf16lo(bv[j]), b1 = bf16hi(bv[j]);
@@ -1016,7 +1018,7 @@ __device__ __forceinline__ MegaAttnMeta mega_attention_meta(const MegaArgs& m, i
   return t;
 }
 __device__ __forceinline__ void mega_attention_prefetch(const MegaArgs& m, const bf16* kv_layer, const MegaAttnMeta& t, unsigned char* scratch) {
-  if (t.n_old <= 0) return;
+  if (t.n_old <= 0) { asm volatile("cp.async.commit_group;" ::: "memory"); return; }     // always one group: see cp.async.wait_group 1 in the in_proj norm
   bf16* ks = reinterpret_cast<bf16*>(scratch);
   bf16* vs = ks + kCH * kKStride;
   const bf16* kp = kv_layer + (((size_t)t.page * 2 + 0) * m.Hkv + t.g) * kCH * kHD;
@@ -1161,6 +1163,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   unsigned char* ring = smem_m;
   float* part = reinterpret_cast<float*>(smem_m + (size_t)S * kMegaStageBytes);
   unsigned char* attn_scratch = smem_m + (size_t)S * kMegaStageBytes + m.part_bytes;
+  bf16* nbuf = reinterpret_cast<bf16*>(attn_scratch + kMegaAttnBytes);   // [2 buffers][weight | bias][D]: norm parameters, copied a layer ahead
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kW3); }
     mbar_fence_init();
@@ -1171,10 +1174,11 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
 
   if (warp == kW3) {
     // ===== producer: the whole step's weights, in consumption order =====
-    const uint64_t pol = l2_evict_first_policy();
+    const uint64_t pol = m.evict_first ? l2_evict_first_policy() : 0ull;
     int gst = 0;
-    for (int li = 0; li < m.n_layer; ++li) {
-      const MegaLayer& L = m.layers[li];
+    MegaLayer L = m.layers[0], Lnext = L;
+    for (int li = 0; li < m.n_layer; ++li, L = Lnext) {
+      if (li + 1 < m.n_layer) Lnext = m.layers[li + 1];       // the next layer's pointers are on their way while this one streams
       mega_fill(a, m, R);
       a.W = L.in_proj; a.N = nqkv; a.K = m.D;
       mega_produce<EPI_QKV>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
@@ -1197,6 +1201,18 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   int ph = 0, gst = 0, stamp_i = 0;
   const MegaAttnMeta ameta = mega_attention_meta(m, blockIdx.x, R * m.Hkv * m.nsplit);
   const bool stamping = m.timeline && blockIdx.x == 0;
+  // norm parameters -> shared memory: one 16-byte cp.async per consumer thread and buffer half
+  auto norm_prefetch = [&](int buf, const bf16* w, const bf16* b) {
+    const int chunks = m.D / 8;
+    bf16* dstw = nbuf + (size_t)buf * 2 * m.D;
+    for (int q = threadIdx.x; q < 2 * chunks; q += kW3 * 32) {
+      const bf16* src = q < chunks ? w + q * 8 : (b ? b + (q - chunks) * 8 : nullptr);
+      if (src) cp_async16(dstw + q * 8, src);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  norm_prefetch(0, m.layers[0].norm_w, m.layers[0].norm_b);
+  norm_prefetch(1, m.layers[0].norm2_w, m.layers[0].norm2_b);
 #define MEGA_STAMP() do { if (stamping && threadIdx.x == 0 && stamp_i < 126) m.timeline[stamp_i] = gtime(); ++stamp_i; } while (0)
 #define MEGA_STAMP_SLOT() ((stamping && stamp_i < 126) ? &m.timeline[stamp_i++] : (++stamp_i, (unsigned long long*)nullptr))
 #define TAG(p) mega_tag(epoch, nph, (p))
@@ -1220,16 +1236,17 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   MEGA_STAMP();
   ph = 1;
 
-  for (int li = 0; li < m.n_layer; ++li) {
-    const MegaLayer& L = m.layers[li];
+  MegaLayer L = m.layers[0], Lnext = L;
+  for (int li = 0; li < m.n_layer; ++li, L = Lnext) {
+    if (li + 1 < m.n_layer) Lnext = m.layers[li + 1];         // pointers of the next layer: loaded a layer before they are needed
     // A: norm -> in_proj -> RoPE -> KV append (+ q)
     mega_fill(a, m, R);
-    a.W = L.in_proj; a.N = nqkv; a.K = m.D; a.ldx = m.D; a.nw = L.norm_w; a.nb = L.norm_b; a.kv_layer = L.kv_layer;
+    a.W = L.in_proj; a.N = nqkv; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = L.norm_b ? nbuf + m.D : nullptr; a.kv_layer = L.kv_layer;
     mega_attention_prefetch(m, L.kv_layer, ameta, attn_scratch);
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       mega_consume<R, 1, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
-                                               nullptr, m.qt, m.kvt, slot);
+                                               nullptr, m.qt, m.kvt, slot, 1);
     }
     MEGA_STAMP(); ++ph;
     // B: attention over the paged cache
@@ -1240,6 +1257,8 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
                             unit == (int)blockIdx.x ? slot : nullptr);
     }
     MEGA_STAMP(); ++ph;
+    // buffer 0 is free since the in_proj phase: the next layer's first norm (or the final norm) starts its way to shared memory
+    if (li + 1 < m.n_layer) norm_prefetch(0, Lnext.norm_w, Lnext.norm_b); else norm_prefetch(0, m.normf_w, m.normf_b);
     // C/D: out_proj (twice in the reference); the slice stays in the ring between the passes
     {
       const int gst0 = gst;
@@ -1265,13 +1284,14 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
     }
     // E: norm2 -> fc1 -> value * silu(gate)
     mega_fill(a, m, R);
-    a.W = L.fc1; a.N = 2 * m.F; a.K = m.D; a.ldx = m.D; a.nw = L.norm2_w; a.nb = L.norm2_b; a.ldy = m.F;
+    a.W = L.fc1; a.N = 2 * m.F; a.K = m.D; a.ldx = m.D; a.nw = nbuf + 2 * m.D; a.nb = L.norm2_b ? nbuf + 3 * m.D : nullptr; a.ldy = m.F;
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       mega_consume<R, 1, 4, PRO_NORM, EPI_SILU>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
                                                 nullptr, nullptr, nullptr, slot);
     }
     MEGA_STAMP(); ++ph;
+    if (li + 1 < m.n_layer) norm_prefetch(1, Lnext.norm2_w, Lnext.norm2_b);
     // F: fc2 + residual
     mega_fill(a, m, R);
     a.W = L.fc2; a.N = m.D; a.K = m.F; a.ldx = m.F; a.ldy = m.D; a.ldr = m.D;
@@ -1288,7 +1308,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   }
   // heads: final norm -> fused heads -> fp32 -> CFG mix
   mega_fill(a, m, R);
-  a.W = m.heads; a.N = m.QV; a.K = m.D; a.ldx = m.D; a.nw = m.normf_w; a.nb = m.normf_b;
+  a.W = m.heads; a.N = m.QV; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = m.normf_b ? nbuf + m.D : nullptr;
   {
     unsigned long long* slot = MEGA_STAMP_SLOT();
     mega_consume<R, 1, 4, PRO_NORM, EPI_HEADS>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, 0u,
@@ -1887,12 +1907,14 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     const int max_items = std::max(((d.d_ff + grid - 1) / grid) * R, ((m.QV + grid - 1) / grid) * R);
     ZB_REQUIRE(ctx, max_items <= kW3 * 32 && ((d.d_model + grid - 1) / grid) * R <= kW3 * 32, "persistent decode: %d epilogue items per CTA", max_items);
   }
-  const size_t attn_bytes = 40 * 1024;
+  const size_t attn_bytes = kMegaAttnBytes + (size_t)4 * d.d_model * sizeof(bf16);   // attention tiles + two norm-parameter buffers
   const size_t avail = 227 * 1024 - 2048;
   int stages = (int)((avail - pb - attn_bytes) / kMegaStageBytes);
   if (stages > kMaxStages) stages = kMaxStages;
   ZB_REQUIRE(ctx, stages >= 3, "persistent decode: not enough shared memory for the ring");
   m.ring_stages = stages; m.part_bytes = (int)pb;
+  static const int evict_first = env_int("ZB_MEGA_EVICT_FIRST", 1);
+  m.evict_first = evict_first;
   const size_t smem = (size_t)stages * kMegaStageBytes + pb + attn_bytes;
   auto launch = [&](auto kernel) -> zb_status {
     static size_t attr = 0;

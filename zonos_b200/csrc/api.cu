@@ -86,6 +86,10 @@ zb_status zb_ctx_destroy(zb_ctx* ctx) {
   if (ctx->tc_ws) cudaFree(ctx->tc_ws);
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
+  for (zb_gen_slab& sl : ctx->gen_slabs) {
+    if (sl.dev) cudaFree(sl.dev);
+    if (sl.host) cudaFreeHost(sl.host);
+  }
   delete ctx;
   return ZB_OK;
 }
@@ -192,6 +196,7 @@ struct zb_gen {
   unsigned* mega_bar = nullptr;     // sync words of the persistent kernel ([1] = epoch of the tagged arena)
   uint32_t* mega_arena = nullptr;   // tagged activation words exchanged between its CTAs
   bool mega = false;
+  int slab = -1;                    // index into ctx->gen_slabs
   cudaGraphExec_t graph = nullptr;
   int64_t launches_per_step = 0;
   int max_steps = 0, steps_enqueued = 0, max_kv = 0;
@@ -257,24 +262,44 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
   g->max_kv = (total + ZB_PAGE_TOKENS - 1) / ZB_PAGE_TOKENS * ZB_PAGE_TOKENS;
   auto fail = [&](zb_status e) { zb_generate_end(g); return e; };
 #define G_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { zb_fail(ctx, ZB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); return fail(ZB_ERR_CUDA); } } while (0)
-  G_CUDA(cudaMalloc(&g->st, sizeof(zb_loop_state)));
-  G_CUDA(cudaHostAlloc(&g->st_host, 16 * sizeof(int32_t), cudaHostAllocMapped));
-  memset(g->st_host, 0, 16 * sizeof(int32_t));
-  g->st_host[0] = desc->prefix_audio_len + 1;
-  G_CUDA(cudaHostGetDevicePointer((void**)&g->st_host_dev, g->st_host, 0));
-  G_CUDA(cudaMalloc(&g->logits, (size_t)B * Q * md.head_vocab * 4));
-  G_CUDA(cudaMalloc(&g->xdec, (size_t)R * md.d_model * 2));
+  // one slab per session (reused across sessions, see zb_gen_slab): loop state | logits | decode residual | layer
+  // table | sync words | tagged activation arena
   g->mega = zb_mega_supported(model, R);
-  if (g->mega) {
-    std::vector<unsigned char> hb(zb_mega_layers_bytes(model));
-    if (zb_status st = zb_mega_layers_build(ctx, model, cache, hb.data())) return fail(st);
-    G_CUDA(cudaMalloc(&g->mega_layers, hb.size()));
-    G_CUDA(cudaMemcpyAsync(g->mega_layers, hb.data(), hb.size(), cudaMemcpyHostToDevice, s));
-    G_CUDA(cudaStreamSynchronize(s));                   // hb is a stack-scoped staging buffer
-    G_CUDA(cudaMalloc(&g->mega_bar, 2 * sizeof(unsigned)));
-    G_CUDA(cudaMemsetAsync(g->mega_bar, 0, 2 * sizeof(unsigned), s));
-    G_CUDA(cudaMalloc(&g->mega_arena, zb_mega_arena_bytes(model, R)));
-    G_CUDA(cudaMemsetAsync(g->mega_arena, 0, zb_mega_arena_bytes(model, R), s));   // tag 0 = never written
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t o_st = 0, o_logits = o_st + up(sizeof(zb_loop_state)), o_x = o_logits + up((size_t)B * Q * md.head_vocab * 4);
+  const size_t o_layers = o_x + up((size_t)R * md.d_model * 2), o_bar = o_layers + up(g->mega ? zb_mega_layers_bytes(model) : 0);
+  const size_t o_arena = o_bar + 256, slab_need = o_arena + up(g->mega ? zb_mega_arena_bytes(model, R) : 0);
+  {
+    int pick = -1;
+    for (size_t i = 0; i < ctx->gen_slabs.size(); ++i)
+      if (!ctx->gen_slabs[i].in_use && (pick < 0 || ctx->gen_slabs[i].dev_bytes >= slab_need)) { pick = (int)i; if (ctx->gen_slabs[i].dev_bytes >= slab_need) break; }
+    if (pick < 0) { ctx->gen_slabs.push_back(zb_gen_slab()); pick = (int)ctx->gen_slabs.size() - 1; }
+    zb_gen_slab& sl = ctx->gen_slabs[pick];
+    sl.in_use = true;
+    g->slab = pick;
+    if (sl.dev_bytes < slab_need) {
+      if (sl.dev) { G_CUDA(cudaStreamSynchronize(s)); G_CUDA(cudaFree(sl.dev)); sl.dev = nullptr; sl.dev_bytes = 0; }
+      G_CUDA(cudaMalloc(&sl.dev, slab_need));
+      sl.dev_bytes = slab_need;
+    }
+    if (!sl.host) {
+      G_CUDA(cudaHostAlloc(&sl.host, 16 * sizeof(int32_t), cudaHostAllocMapped));
+      G_CUDA(cudaHostGetDevicePointer((void**)&sl.host_dev, sl.host, 0));
+    }
+    char* base = (char*)sl.dev;
+    g->st = (zb_loop_state*)(base + o_st); g->logits = (float*)(base + o_logits); g->xdec = (bf16*)(base + o_x);
+    g->st_host = sl.host; g->st_host_dev = sl.host_dev;
+    memset(g->st_host, 0, 16 * sizeof(int32_t));
+    g->st_host[0] = desc->prefix_audio_len + 1;
+    if (g->mega) {
+      g->mega_layers = base + o_layers; g->mega_bar = (unsigned*)(base + o_bar); g->mega_arena = (uint32_t*)(base + o_arena);
+      std::vector<unsigned char> hb(zb_mega_layers_bytes(model));
+      if (zb_status st = zb_mega_layers_build(ctx, model, cache, hb.data())) return fail(st);
+      G_CUDA(cudaMemcpyAsync(g->mega_layers, hb.data(), hb.size(), cudaMemcpyHostToDevice, s));
+      G_CUDA(cudaStreamSynchronize(s));                   // hb is a stack-scoped staging buffer
+      G_CUDA(cudaMemsetAsync(g->mega_bar, 0, 256, s));
+      G_CUDA(cudaMemsetAsync(g->mega_arena, 0, zb_mega_arena_bytes(model, R), s));   // tag 0 = never written
+    }
   }
   const int offset0 = P + 1;
   g->max_steps = desc->T_delayed - offset0;               // model.py:440
@@ -371,13 +396,7 @@ zb_status zb_generate_end(zb_gen* gen) {
   if (!gen) return ZB_OK;
   if (gen->pinned) gen->ctx->scratch_pins--;
   if (gen->graph) cudaGraphExecDestroy(gen->graph);
-  if (gen->st) cudaFree(gen->st);
-  if (gen->st_host) cudaFreeHost(gen->st_host);
-  if (gen->logits) cudaFree(gen->logits);
-  if (gen->xdec) cudaFree(gen->xdec);
-  if (gen->mega_layers) cudaFree(gen->mega_layers);
-  if (gen->mega_bar) cudaFree(gen->mega_bar);
-  if (gen->mega_arena) cudaFree(gen->mega_arena);
+  if (gen->slab >= 0) gen->ctx->gen_slabs[gen->slab].in_use = false;   // the memory stays with the context for the next session
   delete gen;
   return ZB_OK;
 }

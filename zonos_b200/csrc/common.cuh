@@ -16,6 +16,11 @@
 
 typedef __nv_bfloat16 bf16;
 
+// Device + pinned memory of one generate session.  cudaMalloc / cudaFree / cudaFreeHost per session cost up to hundreds
+// of milliseconds on a busy box (measured: zb_generate_end 0.6 - 700 ms), so finished sessions hand their slab back to
+// the context and the next session reuses it.
+struct zb_gen_slab { void* dev = nullptr; size_t dev_bytes = 0; int32_t* host = nullptr; int32_t* host_dev = nullptr; bool in_use = false; };
+
 struct zb_ctx {
   int device = 0;
   int num_sms = ZB_NUM_SMS;
@@ -33,6 +38,7 @@ struct zb_ctx {
   size_t tc_ws_bytes = 0;
   int32_t* counters = nullptr;  // zeroed int32 words for last-CTA-done patterns
   cudaStream_t capture_stream = nullptr;   // graph capture happens here (the caller's stream may be the legacy one)
+  std::vector<zb_gen_slab> gen_slabs;      // session memory, reused across generate calls
 };
 
 extern thread_local std::string g_zb_create_error;

@@ -720,6 +720,7 @@ struct MegaArgs {
   unsigned* sync;         // [1] = epoch: number of live steps this session's tagged buffers have seen
   int ring_stages, part_bytes, evict_first;
   unsigned long long* timeline;   // debug: globaltimer stamps of CTA 0 (2 per phase: inputs ready, work done)
+  unsigned long long* steplog;    // debug: [2*step] start, [2*step+1] end of every step (CTA 0)
 };
 
 constexpr int kMegaStageBytes = 32 * 1024, kMegaAttnBytes = 40 * 1024;
@@ -1216,6 +1217,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
 #define MEGA_STAMP() do { if (stamping && threadIdx.x == 0 && stamp_i < 126) m.timeline[stamp_i] = gtime(); ++stamp_i; } while (0)
 #define MEGA_STAMP_SLOT() ((stamping && stamp_i < 126) ? &m.timeline[stamp_i++] : (++stamp_i, (unsigned long long*)nullptr))
 #define TAG(p) mega_tag(epoch, nph, (p))
+  if (m.steplog && blockIdx.x == 0 && threadIdx.x == 0 && m.loop) m.steplog[2 * min(m.loop->steps, 4000)] = gtime();
   MEGA_STAMP();
   // phase 0: codebook embedding sum (sequential bf16 adds, codec_utils.py:37) for this CTA's columns, both CFG rows
   {
@@ -1317,6 +1319,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   MEGA_STAMP();
   // CTA 0 can only get here after it consumed outputs of every CTA, i.e. after every CTA read the epoch
   if (blockIdx.x == 0 && threadIdx.x == 0) m.sync[1] = epoch + 1;
+  if (m.steplog && blockIdx.x == 0 && threadIdx.x == 0 && m.loop) m.steplog[2 * min(m.loop->steps, 4000) + 1] = gtime();
 #undef MEGA_STAMP
 #undef MEGA_STAMP_SLOT
 #undef TAG
@@ -1821,6 +1824,7 @@ zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden
 
 
 static unsigned long long* g_timeline = nullptr;   // debug: set by zb_debug_timeline
+static unsigned long long* g_steplog = nullptr;    // debug: set by zb_debug_steplog
 
 // ---- persistent decode step (host side) ----
 size_t zb_mega_layers_bytes(const zb_model* model) { return (size_t)model->d.n_layer * sizeof(MegaLayer); }
@@ -1887,7 +1891,7 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     m.kvt = p; p += (size_t)R * 2 * kn_;
   }
   m.attn_part = s.part; m.attn_counters = ctx->counters; m.nsplit = nsplit;
-  m.scale = 1.0f / sqrtf((float)d.head_dim); m.loop = loop; m.sync = sync; m.timeline = g_timeline;
+  m.scale = 1.0f / sqrtf((float)d.head_dim); m.loop = loop; m.sync = sync; m.timeline = g_timeline; m.steplog = g_steplog;
   ZB_REQUIRE(ctx, cfg_scale != 1.0f, "persistent decode expects CFG rows");
   const int grid = ctx->num_sms;
   // partial-sum buffer: the largest padded row count x k-slices over all matrices of the step
@@ -1938,6 +1942,7 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
 
 // ---- diagnostics: launch ONE production kernel on scratch activations (bench.py roofline leg) ----
 extern "C" ZB_API zb_status zb_debug_timeline(unsigned long long* dev_buf) { g_timeline = dev_buf; return ZB_OK; }
+extern "C" ZB_API zb_status zb_debug_steplog(unsigned long long* dev_buf) { g_steplog = dev_buf; return ZB_OK; }
 
 extern "C" zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows, int32_t iters,
                                      zb_stream stream) {

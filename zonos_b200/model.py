@@ -5,6 +5,7 @@ plus `embed_codes`, `apply_heads`, `setup_cache`, `device`.  `generate` runs pre
 loop (embed -> backbone -> heads/CFG -> sampler -> EOS/delay bookkeeping) and the early-exit test on the device
 through `zb_generate_*`; the host only enqueues CUDA-graph replays and polls a flag.
 """
+import os
 import ctypes as C
 import json
 from typing import Callable
@@ -190,12 +191,19 @@ class Zonos(nn.Module):
         Lc = cond.shape[1]
         audio_len = P + max_new_tokens
         seq_len = Lc + audio_len + Q                                         # model.py:409
+        _dbg = os.environ.get("ZB_HOST_TIMES")
+        if _dbg:
+            import time as _time
+            torch.cuda.synchronize(device); _t = [_time.perf_counter()]
+            def _mark():
+                torch.cuda.synchronize(device); _t.append(_time.perf_counter())
         params = self.setup_cache(batch_size=2 * B, max_seqlen=seq_len)
         codes = torch.full((B, Q, audio_len), -1, dtype=torch.int64, device=device)
         if audio_prefix_codes is not None:
             codes[..., :P] = audio_prefix_codes.to(device)
         delayed = apply_delay_pattern(codes, self.masked_token_id).contiguous()
         T_delayed = delayed.shape[2]
+        if _dbg: _mark()
 
         n_calls = T_delayed - P                                              # sample calls at most (1 + max_steps - 1)
         if seed is None:
@@ -225,6 +233,7 @@ class Zonos(nn.Module):
         prog = _lib.zb_gen_progress()
         with ctx.lock:
             ctx.check(lib.zb_generate_begin(ctx.handle, self._native_model(), C.byref(cache), C.byref(desc), C.byref(gen), stream))
+            if _dbg: _mark()
             try:
                 max_steps = T_delayed - (P + 1)
                 first_frame = delayed[..., P + 1:P + 2]
@@ -254,12 +263,18 @@ class Zonos(nn.Module):
                         if not callback(first_frame, prog.steps, max_steps):
                             break
                 ctx.check(lib.zb_generate_poll(gen, C.byref(prog), stream))
+                if _dbg: _mark()
             finally:
                 lib.zb_generate_end(gen)
+        if _dbg: _mark()
         offset = int(prog.offset)
         if trace is not None:
             trace.update(delayed=delayed.clone(), offset=offset, steps=int(prog.steps), logits=logits_trace, seed=seed)
-        return self._finalize(delayed, offset)
+        out = self._finalize(delayed, offset)
+        if _dbg:
+            _mark()
+            print("host times ms: setup %.1f begin+prefill %.1f steps %.1f end %.1f finalize %.1f" % tuple((b - a) * 1e3 for a, b in zip(_t[:-1], _t[1:])))
+        return out
 
 
     # ---------------------------------------------------------------- streaming -----------

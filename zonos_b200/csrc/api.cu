@@ -281,6 +281,7 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
       if (sl.dev) { G_CUDA(cudaStreamSynchronize(s)); G_CUDA(cudaFree(sl.dev)); sl.dev = nullptr; sl.dev_bytes = 0; }
       G_CUDA(cudaMalloc(&sl.dev, slab_need));
       sl.dev_bytes = slab_need;
+      sl.layers.clear();
     }
     if (!sl.host) {
       G_CUDA(cudaHostAlloc(&sl.host, 16 * sizeof(int32_t), cudaHostAllocMapped));
@@ -295,8 +296,11 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
       g->mega_layers = base + o_layers; g->mega_bar = (unsigned*)(base + o_bar); g->mega_arena = (uint32_t*)(base + o_arena);
       std::vector<unsigned char> hb(zb_mega_layers_bytes(model));
       if (zb_status st = zb_mega_layers_build(ctx, model, cache, hb.data())) return fail(st);
-      G_CUDA(cudaMemcpyAsync(g->mega_layers, hb.data(), hb.size(), cudaMemcpyHostToDevice, s));
-      G_CUDA(cudaStreamSynchronize(s));                   // hb is a stack-scoped staging buffer
+      if (sl.layers != hb || sl.layers_off != o_layers) {  // same model and cache as the slab's last session: already there
+        sl.layers = hb; sl.layers_off = o_layers;
+        G_CUDA(cudaMemcpyAsync(g->mega_layers, sl.layers.data(), hb.size(), cudaMemcpyHostToDevice, s));
+        G_CUDA(cudaStreamSynchronize(s));                 // pageable source: keep the copy simple and finished
+      }
       G_CUDA(cudaMemsetAsync(g->mega_bar, 0, 256, s));
       G_CUDA(cudaMemsetAsync(g->mega_arena, 0, zb_mega_arena_bytes(model, R), s));   // tag 0 = never written
     }

@@ -19,7 +19,10 @@ typedef __nv_bfloat16 bf16;
 // Device + pinned memory of one generate session.  cudaMalloc / cudaFree / cudaFreeHost per session cost up to hundreds
 // of milliseconds on a busy box (measured: zb_generate_end 0.6 - 700 ms), so finished sessions hand their slab back to
 // the context and the next session reuses it.
-struct zb_gen_slab { void* dev = nullptr; size_t dev_bytes = 0; int32_t* host = nullptr; int32_t* host_dev = nullptr; bool in_use = false; };
+struct zb_gen_slab {
+  void* dev = nullptr; size_t dev_bytes = 0; int32_t* host = nullptr; int32_t* host_dev = nullptr; bool in_use = false;
+  std::vector<unsigned char> layers; size_t layers_off = 0;   // host copy of the layer table last uploaded into this slab
+};
 
 struct zb_ctx {
   int device = 0;

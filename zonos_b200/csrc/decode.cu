@@ -705,6 +705,9 @@ __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
 // passes, so it is read from HBM once.
 // ================================================================================================================
 struct MegaLayer { const bf16 *norm_w, *norm_b, *in_proj, *out_proj, *norm2_w, *norm2_b, *fc1, *fc2; bf16* kv_layer; };
+// what a thread's in_proj epilogue item needs besides the dot products: position, RoPE cos/sin, KV page.  The same in
+// every layer of a step, so it is fetched once per step (three dependent global loads otherwise trail every in_proj)
+struct MegaQkvPre { int pos, page; float2 cs; bool valid; };
 
 struct MegaArgs {
   const MegaLayer* layers; int n_layer;
@@ -818,7 +821,7 @@ template <int R, int NC, int RW, int PRO, int EPI>
 __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* ring, float* part, uint64_t* full_bar, uint64_t* empty_bar,
                                              float (*red)[kW3][4], int S, int& gst, bool release, int warp, int lane,
                                              const uint32_t* xt, uint32_t tag_in, uint32_t* yt, uint32_t tag_out, const uint32_t* rt, uint32_t* qt,
-                                             uint32_t* kvt, unsigned long long* stamp, int norm_pending = 0) {
+                                             uint32_t* kvt, unsigned long long* stamp, int norm_pending = 0, const MegaQkvPre* qkv_pre = nullptr) {
   constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
   constexpr int Kc = NC * 256;
   const int K = a.K, row_bytes = K * 2;
@@ -910,7 +913,9 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   int pre_pos = 0, pre_page = 0;
   if (e_on) {
     if (EPI == EPI_RESID) pre_resid = untag(ld_relaxed_u32(rt + (size_t)ei * a.ldr + en0));   // validated by this CTA in an earlier phase
-    if (EPI == EPI_QKV) {
+    if (EPI == EPI_QKV && qkv_pre && qkv_pre->valid) {
+      pre_pos = qkv_pre->pos; pre_page = qkv_pre->page; pre_cs = qkv_pre->cs;
+    } else if (EPI == EPI_QKV) {
       pre_pos = a.lengths[ei];
       const int qn_ = a.Hq * a.hd, kn_ = a.Hkv * a.hd;
       if (en0 < qn_ + kn_) {
@@ -1007,15 +1012,16 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
 
 // K/V of the tokens cached by EARLIER steps for this CTA's first attention unit of the layer: issued before the
 // in_proj phase so the tile is already in shared memory when the attention phase starts
-struct MegaAttnMeta { int n_old, page, g; };                  // step constants of this CTA's first attention unit
+struct MegaAttnMeta { int n_old, page, g, kv_len; };          // step constants of this CTA's first attention unit
 __device__ __forceinline__ MegaAttnMeta mega_attention_meta(const MegaArgs& m, int unit, int nunits) {
-  MegaAttnMeta t; t.n_old = 0; t.page = 0; t.g = 0;
+  MegaAttnMeta t; t.n_old = 0; t.page = 0; t.g = 0; t.kv_len = 0;
   if (unit >= nunits) return t;
   const int split = unit % m.nsplit, r = unit / (m.nsplit * m.Hkv);
   t.g = (unit / m.nsplit) % m.Hkv;
   const int kv_len = m.lengths[r] + 1;
+  t.kv_len = kv_len;
   t.n_old = max(0, min(kCH, kv_len - 1 - split * kCH));
-  if (t.n_old > 0) t.page = m.page_table[(size_t)r * m.max_pages + split];
+  if (split * kCH < kv_len) t.page = m.page_table[(size_t)r * m.max_pages + split];
   return t;
 }
 __device__ __forceinline__ void mega_attention_prefetch(const MegaArgs& m, const bf16* kv_layer, const MegaAttnMeta& t, unsigned char* scratch) {
@@ -1035,7 +1041,8 @@ __device__ __forceinline__ void mega_attention_prefetch(const MegaArgs& m, const
 }
 
 __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf16* kv_layer, int unit, unsigned char* scratch, int warp, int lane,
-                                                    bool prefetched, uint32_t tag_in, uint32_t tag_out, unsigned long long* stamp) {
+                                                    const MegaAttnMeta* first, uint32_t tag_in, uint32_t tag_out, unsigned long long* stamp) {
+  const bool prefetched = first != nullptr;                            // this CTA's first unit: its step constants are in *first
   bf16* ks = reinterpret_cast<bf16*>(scratch);                         // [64][136]
   bf16* vs = ks + kCH * kKStride;                                      // [64][128]
   float* qs = reinterpret_cast<float*>(vs + kCH * kHD);                // [8][128]
@@ -1043,11 +1050,11 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
   int* s_last = reinterpret_cast<int*>(ps + 8 * kCH);
   const int G = m.Hq / m.Hkv;
   const int split = unit % m.nsplit, g = (unit / m.nsplit) % m.Hkv, r = unit / (m.nsplit * m.Hkv);
-  const int kv_len = m.lengths[r] + 1;
+  const int kv_len = first ? first->kv_len : m.lengths[r] + 1;
   const int nact = (kv_len + kCH - 1) / kCH;
   if (split >= nact) return;                                            // uniform for the CTA
   const int k0 = split * kCH, nk = min(kCH, kv_len - k0);
-  const int page = m.page_table[(size_t)r * m.max_pages + split];
+  const int page = first ? first->page : m.page_table[(size_t)r * m.max_pages + split];
   const bf16* kp = kv_layer + (((size_t)page * 2 + 0) * m.Hkv + g) * kCH * kHD;
   const bf16* vp = kv_layer + (((size_t)page * 2 + 1) * m.Hkv + g) * kCH * kHD;
   // tokens cached by earlier steps were prefetched (mega_attention_prefetch, before the in_proj phase) when
@@ -1214,6 +1221,26 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   };
   norm_prefetch(0, m.layers[0].norm_w, m.layers[0].norm_b);
   norm_prefetch(1, m.layers[0].norm2_w, m.layers[0].norm2_b);
+  MegaQkvPre qkv_pre; qkv_pre.valid = false; qkv_pre.pos = 0; qkv_pre.page = 0; qkv_pre.cs = make_float2(1.f, 0.f);
+  {
+    mega_fill(a, m, R);
+    a.N = nqkv; a.K = m.D;
+    int u_begin, nrows;
+    mega_slice<EPI_QKV>(a, u_begin, nrows);
+    const int et = threadIdx.x;
+    if (et < (nrows / 2) * R) {
+      const int ej = et / R, ei = et % R;
+      int en0, en1;
+      unit_rows<EPI_QKV>(a, u_begin + ej, en0, en1);
+      qkv_pre.pos = m.lengths[ei];
+      if (en0 < qn + m.Hkv * m.hd) {
+        const int ri = m.rope_interleaved ? (en0 % m.hd) / 2 : (en0 % m.hd);
+        qkv_pre.cs = *reinterpret_cast<const float2*>(m.rope + ((size_t)min(qkv_pre.pos, m.rope_len - 1) * (m.hd / 2) + ri) * 2);
+      }
+      if (en0 >= qn) qkv_pre.page = m.page_table[(size_t)ei * m.max_pages + qkv_pre.pos / ZB_PAGE_TOKENS];
+      qkv_pre.valid = true;
+    }
+  }
 #define MEGA_STAMP() do { if (stamping && threadIdx.x == 0 && stamp_i < 126) m.timeline[stamp_i] = gtime(); ++stamp_i; } while (0)
 #define MEGA_STAMP_SLOT() ((stamping && stamp_i < 126) ? &m.timeline[stamp_i++] : (++stamp_i, (unsigned long long*)nullptr))
 #define TAG(p) mega_tag(epoch, nph, (p))
@@ -1248,14 +1275,14 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       mega_consume<R, 1, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
-                                               nullptr, m.qt, m.kvt, slot, 1);
+                                               nullptr, m.qt, m.kvt, slot, 1, &qkv_pre);
     }
     MEGA_STAMP(); ++ph;
     // B: attention over the paged cache
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       for (int unit = blockIdx.x; unit < R * m.Hkv * m.nsplit; unit += gridDim.x)
-        mega_attention_unit(m, L.kv_layer, unit, attn_scratch, warp, lane, unit == (int)blockIdx.x, TAG(ph - 1), TAG(ph),
+        mega_attention_unit(m, L.kv_layer, unit, attn_scratch, warp, lane, unit == (int)blockIdx.x ? &ameta : nullptr, TAG(ph - 1), TAG(ph),
                             unit == (int)blockIdx.x ? slot : nullptr);
     }
     MEGA_STAMP(); ++ph;

@@ -14,7 +14,7 @@ lib = C.CDLL(_lib.LIB_PATH); lib.zb_debug_timeline.argtypes = [C.c_void_p]
 B = int(os.environ.get("ZB_TL_B", "1"))
 cond = make_conditioning(2 * B, 160, 2048).to(dev)
 m.generate(cond, max_new_tokens=40, seed=1)
-buf = torch.zeros(128, dtype=torch.int64, device=dev)
+buf = torch.zeros(512, dtype=torch.int64, device=dev)
 lib.zb_debug_timeline(C.c_void_p(buf.data_ptr()))
 m.generate(cond, max_new_tokens=400, seed=1)          # the buffer keeps the stamps of the LAST step (kv_len ~ 570)
 lib.zb_debug_timeline(C.c_void_p(0))
@@ -29,3 +29,8 @@ for layer in range(3):
         row.append(f"{ph}:{work}+{bar}")
     print(f"layer {layer}: " + "  ".join(row) + "   (work ns + wait ns)")
 print("layer period (layer1 start -> layer2 start):", t[2 + 24] - t[2 + 12], "ns")
+for name, off in (("in_proj", 200), ("fc1", 220)):
+    x = t[off:off + 9]
+    if x[0] > 0:
+        lab = ["inputs ready", "stats issued", "norm params in smem", "LN barrier", "normalized", "first stage", "stages done", "final barrier", "epilogue done"]
+        print(f"layer 1 {name}: " + "  ".join(f"{l} +{v - x[0]}" for l, v in zip(lab[1:], x[1:])))

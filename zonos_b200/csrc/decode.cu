@@ -821,7 +821,8 @@ template <int R, int NC, int RW, int PRO, int EPI>
 __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* ring, float* part, uint64_t* full_bar, uint64_t* empty_bar,
                                              float (*red)[kW3][4], int S, int& gst, bool release, int warp, int lane,
                                              const uint32_t* xt, uint32_t tag_in, uint32_t* yt, uint32_t tag_out, const uint32_t* rt, uint32_t* qt,
-                                             uint32_t* kvt, unsigned long long* stamp, int norm_pending = 0, const MegaQkvPre* qkv_pre = nullptr) {
+                                             uint32_t* kvt, unsigned long long* stamp, int norm_pending = 0, const MegaQkvPre* qkv_pre = nullptr, unsigned long long* dbg = nullptr) {
+#define DBG(i) do { if (dbg && threadIdx.x == 0) dbg[i] = gtime(); } while (0)
   constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
   constexpr int Kc = NC * 256;
   const int K = a.K, row_bytes = K * 2;
@@ -850,6 +851,7 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
     if (spins > kMegaSpinLimit) asm volatile("trap;");
   }
   if (stamp && threadIdx.x == 0) *stamp = gtime();
+  DBG(0);
   if (PRO == PRO_NORM) {
     float mean[R], rstd[R];
 #pragma unroll
@@ -864,15 +866,21 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
     // the norm parameters sit in shared memory (copied there a layer ahead: a global load issued here would queue
     // behind the saturated weight stream for microseconds); this thread's copies are complete after the wait, all
     // threads' after the barrier
+    DBG(1);
     if (norm_pending == 0) asm volatile("cp.async.wait_group 0;" ::: "memory"); else asm volatile("cp.async.wait_group 1;" ::: "memory");
+    DBG(2);
     asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+    DBG(3);
+    // every warp sums the KS per-warp partials with a fixed shuffle tree (lane q holds slice q): far fewer issue
+    // slots than a serial loop in each of the 16 warps, and the same bits in every warp
+    const float inv_k = 1.0f / (float)K;                        // K is a power of two: multiplying is exact
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      float tot = 0.f, tsq = 0.f;
-      for (int q = 0; q < KS; ++q) { tot += red[0][q][i]; tsq += red[1][q][i]; }
-      const float mu = tot / (float)K;
+      const float tot = warp_sum(lane < KS ? red[0][lane][i] : 0.f);
+      const float tsq = warp_sum(lane < KS ? red[1][lane][i] : 0.f);
+      const float mu = tot * inv_k;
       mean[i] = (a.norm_kind == ZB_NORM_LAYERNORM) ? mu : 0.f;
-      const float var = (a.norm_kind == ZB_NORM_LAYERNORM) ? fmaxf(tsq / (float)K - mu * mu, 0.f) : tsq / (float)K;
+      const float var = (a.norm_kind == ZB_NORM_LAYERNORM) ? fmaxf(tsq * inv_k - mu * mu, 0.f) : tsq * inv_k;
       rstd[i] = rsqrtf(var + a.eps);
     }
 #pragma unroll
@@ -892,6 +900,7 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
       }
     }
   }
+  DBG(4);
   unsigned long long x2[R][NC * 4];
 #pragma unroll
   for (int i = 0; i < R; ++i)
@@ -901,7 +910,7 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   // ---- operands of this thread's epilogue (residual value, RoPE cos/sin, KV page): fetched NOW so their L2 round
   // trips overlap the weight streaming instead of trailing it ----
   const bool cfg = (EPI == EPI_HEADS && a.cfg_scale != 1.0f);
-  const int rows_out = cfg ? a.B : a.M;
+  const int rows_out = cfg ? a.B : R;                          // a.M == R in the persistent kernel
   const int nu = kPairs ? nrows / 2 : nrows;
   const int et = threadIdx.x;                                 // one epilogue item per thread (host guarantees nu*rows_out <= 512)
   const bool e_on = et < nu * rows_out;
@@ -933,10 +942,13 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   const uint32_t lane_base = smem_u32(ring) + (uint32_t)(rg * RW) * row_bytes + (uint32_t)(koff + lane * 8) * 2;
   const uint32_t part_lane = smem_u32(part) + (uint32_t)((((rg * RW + my_idx / R) * KS + ks) * R + my_idx % R) * 4);
   const uint32_t part_stage = (uint32_t)(RPS * KS * R * 4);
-  for (int st = 0; st < nstage; ++st, ++gst) {
-    const uint32_t slot = (uint32_t)(gst % S), phase = (uint32_t)((gst / S) & 1);
-    mbar_wait_u32(full0 + slot * 8, phase);
-    const uint32_t src = lane_base + slot * kMegaStageBytes;
+  uint32_t slot = (uint32_t)(gst % S), phase = (uint32_t)((gst / S) & 1);   // advanced incrementally: no division per stage
+  uint32_t src = lane_base + slot * kMegaStageBytes, fb = full0 + slot * 8, eb = empty0 + slot * 8;
+  uint32_t part_dst = part_lane;
+  gst += nstage;
+  for (int st = 0; st < nstage; ++st) {
+    mbar_wait_u32(fb, phase);
+    if (st == 0) DBG(5);
     unsigned long long acc2[V];
 #pragma unroll
     for (int q = 0; q < V; ++q) acc2[q] = 0ull;
@@ -955,14 +967,19 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
       }
     }
     __syncwarp();
-    if (release && lane == 0) mbar_arrive_u32(empty0 + slot * 8);
+    if (release && lane == 0) mbar_arrive_u32(eb);
     float acc[V];
 #pragma unroll
     for (int q = 0; q < V; ++q) acc[q] = sum_f32x2(acc2[q]);
     warp_reduce_multi<V>(acc);
-    if (writer) sts32(part_lane + st * part_stage, acc[0]);
+    if (writer) sts32(part_dst, acc[0]);
+    part_dst += part_stage;
+    if (++slot == (uint32_t)S) { slot = 0; phase ^= 1u; src = lane_base; fb = full0; eb = empty0; }
+    else { src += kMegaStageBytes; fb += 8; eb += 8; }
   }
+  DBG(6);
   asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  DBG(7);
 
   if (e_on) {
     float v0 = 0.f, v1 = 0.f, u0 = 0.f;
@@ -1008,6 +1025,8 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
       gemv_epilogue<EPI>(a, ei, en0, en1, kPairs, v0, v1, u0, 0.f);
     }
   }
+  DBG(8);
+#undef DBG
 }
 
 // K/V of the tokens cached by EARLIER steps for this CTA's first attention unit of the layer: issued before the
@@ -1275,7 +1294,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       mega_consume<R, 1, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
-                                               nullptr, m.qt, m.kvt, slot, 1, &qkv_pre);
+                                               nullptr, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
     }
     MEGA_STAMP(); ++ph;
     // B: attention over the paged cache
@@ -1317,7 +1336,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       mega_consume<R, 1, 4, PRO_NORM, EPI_SILU>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
-                                                nullptr, nullptr, nullptr, slot);
+                                                nullptr, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 220 : nullptr);
     }
     MEGA_STAMP(); ++ph;
     if (li + 1 < m.n_layer) norm_prefetch(1, Lnext.norm2_w, Lnext.norm2_b);

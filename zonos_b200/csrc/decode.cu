@@ -1153,16 +1153,20 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
   asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
   if (*s_last && warp < G) {
     const float* base = m.attn_part + (((size_t)r * m.Hq + head) * m.nsplit) * kPart;
-    float M = -INFINITY;
-    for (int sp = 0; sp < nact; ++sp) M = fmaxf(M, __ldcg(base + (size_t)sp * kPart + kHD));
-    float L = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // one pass with a running maximum (online softmax merge): the loads of all splits are independent, so the merge
+    // costs one L2 round trip instead of two (maximum first, values second)
+    float M = -INFINITY, L = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int sp = 0; sp < nact; ++sp) {
       const float* ps_ = base + (size_t)sp * kPart;
-      const float w = __expf(__ldcg(ps_ + kHD) - M);
-      L = fmaf(__ldcg(ps_ + kHD + 1), w, L);
+      const float ms = __ldcg(ps_ + kHD), ls = __ldcg(ps_ + kHD + 1);
       const float4 ov = __ldcg(reinterpret_cast<const float4*>(ps_ + lane * 4));
-      acc[0] = fmaf(ov.x, w, acc[0]); acc[1] = fmaf(ov.y, w, acc[1]);
-      acc[2] = fmaf(ov.z, w, acc[2]); acc[3] = fmaf(ov.w, w, acc[3]);
+      const float Mn = fmaxf(M, ms);
+      const float so = __expf(M - Mn), sn = __expf(ms - Mn);   // M = -inf on the first split: so = 0
+      L = fmaf(ls, sn, L * so);
+      acc[0] = fmaf(ov.x, sn, acc[0] * so); acc[1] = fmaf(ov.y, sn, acc[1] * so);
+      acc[2] = fmaf(ov.z, sn, acc[2] * so); acc[3] = fmaf(ov.w, sn, acc[3] * so);
+      M = Mn;
     }
     const float inv = 1.0f / L;
     const uint4 outv = make_uint4(tag_word(acc[0] * inv, tag_out), tag_word(acc[1] * inv, tag_out), tag_word(acc[2] * inv, tag_out),

@@ -13,7 +13,7 @@ m.generate(cond, max_new_tokens=64, seed=1)
 import ctypes as C, numpy as np
 from zonos_b200 import _lib
 lib = C.CDLL(_lib.LIB_PATH); lib.zb_debug_steplog.argtypes = [C.c_void_p]
-log = torch.zeros(8200, dtype=torch.int64, device=dev)
+log = torch.zeros(16400 + 8 * 4001, dtype=torch.int64, device=dev)
 lib.zb_debug_steplog(C.c_void_p(log.data_ptr()))
 out = []
 for i in range(reps):
@@ -25,7 +25,12 @@ for i in range(reps):
     e1.record()
     torch.cuda.synchronize()
     out.append((round(e0.elapsed_time(e1), 1), round((time.perf_counter() - t0) * 1e3, 1), c.shape[-1]))
-    t = log.cpu().numpy().reshape(-1, 2)[1:N - 2]
+    full = log.cpu().numpy()
+    t = full[:8200].reshape(-1, 2)[1:N - 2]
+    ts = full[8200:16400].reshape(-1, 2)[1:N - 2]
+    fine = full[16400:16400 + 8 * 4001].reshape(-1, 8)[1:N - 2]
+    print("   sampler stages after start (p50 us): logits+penalty %.1f softmax %.1f min-p %.1f race %.1f syncthreads %.1f bookkeeping %.1f fence+atomic %.1f end %.1f" % tuple([np.median(fine[:, k] - ts[:, 0]) / 1e3 for k in range(7)] + [np.median(ts[:, 1] - ts[:, 0]) / 1e3]))
+    print(f"   sampler: kernel end -> sampler start p50 {np.median(ts[:, 0] - t[:, 1]) / 1e3:.1f} us, sampler run p50 {np.median(ts[:, 1] - ts[:, 0]) / 1e3:.1f} us, sampler end -> next kernel start p50 {np.median(t[1:, 0] - ts[:-1, 1]) / 1e3:.1f} us")
     dur = (t[:, 1] - t[:, 0]) / 1e3
     gap = (t[1:, 0] - t[:-1, 1]) / 1e3
     print(f"run {i}: {out[-1][0]} ms; step kernel us: p50 {np.median(dur):.0f} p90 {np.percentile(dur, 90):.0f} max {dur.max():.0f}; gap between steps us: p50 {np.median(gap):.0f} p90 {np.percentile(gap, 90):.0f} max {gap.max():.0f}; first/last quarter kernel p50 {np.median(dur[:N//4]):.0f}/{np.median(dur[-N//4:]):.0f}")

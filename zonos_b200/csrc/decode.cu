@@ -1993,6 +1993,7 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
 // ---- diagnostics: launch ONE production kernel on scratch activations (bench.py roofline leg) ----
 extern "C" ZB_API zb_status zb_debug_timeline(unsigned long long* dev_buf) { g_timeline = dev_buf; return ZB_OK; }
 extern "C" ZB_API zb_status zb_debug_steplog(unsigned long long* dev_buf) { g_steplog = dev_buf; return ZB_OK; }
+unsigned long long* zb_debug_steplog_ptr() { return g_steplog; }
 
 extern "C" zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows, int32_t iters,
                                      zb_stream stream) {

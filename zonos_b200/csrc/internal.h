@@ -63,6 +63,7 @@ zb_status zb_launch_heads(zb_ctx* ctx, const zb_model* model, const bf16* hidden
 size_t zb_backbone_scratch_bytes(const zb_model* model, int R, int T, int max_kv_len);
 // persistent single-launch decode step (decode.cu)
 bool zb_mega_supported(const zb_model* model, int R);
+unsigned long long* zb_debug_steplog_ptr();                  // debug (zb_debug_steplog), nullptr normally
 size_t zb_mega_layers_bytes(const zb_model* model);
 size_t zb_mega_arena_bytes(const zb_model* model, int R);     // tagged activation words of one generate session (zeroed by the caller)
 zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf);

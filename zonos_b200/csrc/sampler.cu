@@ -26,8 +26,8 @@ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_
   uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
   c0 = n0; c1 = n1; c2 = n2; c3 = n3;
 }
-// Philox4x32-10; returns the first output word for counter (a,b,c,d)
-__device__ __forceinline__ uint32_t philox(uint64_t seed, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+// Philox4x32-10: the four output words for counter (a,b,c,d)
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -35,12 +35,19 @@ __device__ __forceinline__ uint32_t philox(uint64_t seed, uint32_t a, uint32_t b
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
-  return a;
+  return make_uint4(a, b, c, d);
 }
-__device__ __forceinline__ float exp1_draw(uint64_t seed, uint64_t draw, uint32_t row, uint32_t col) {
-  uint32_t x = philox(seed, (uint32_t)draw, (uint32_t)(draw >> 32), row, col);
+// p / s for p >= 0, s > 0 with the IEEE result of the plain division: +0 / s is +0, and skipping it matters - a zero
+// operand sends the fp32 division down its slow path (~100 instructions), and after softmax / min-p most of a row IS zero
+__device__ __forceinline__ float div_pos(float p, float s) { return p == 0.0f ? 0.0f : p / s; }
+__device__ __forceinline__ float exp1_from_bits(uint32_t x) {
   float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
   return -__logf(u);
+}
+// Exp(1) draws for the columns col = j*32 + lane, j = 4*jb .. 4*jb+3, of row `row` in sample call `draw`: one Philox
+// call (counter (draw, row, jb*32 + lane)) serves four columns of the lane
+__device__ __forceinline__ uint4 exp1_block(uint64_t seed, uint64_t draw, uint32_t row, uint32_t jb, uint32_t lane) {
+  return philox4(seed, (uint32_t)draw, (uint32_t)(draw >> 32), row, jb * 32u + lane);
 }
 
 struct SampleArgs {
@@ -68,9 +75,13 @@ struct SampleArgs {
   int prefix_len;             // Lc + P + 1 (first only)
   int32_t* mirror;            // host-mapped progress words (offset, step_idx, done, steps)
   unsigned* reset_word;       // grid-barrier counter of the persistent decode kernel: zeroed after every step
+  unsigned long long* steplog; // debug: [8200 + 2*step] start (after the dependency wait), +1 end (zb_debug_steplog)
 };
 
-__global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
+// kThreads = 32 * (most codebooks the launch may have): 288 for the 9 codebooks of Zonos leaves 224 registers per thread
+// (the row lives in registers: 33 values per lane plus temporaries - 128 registers spill)
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) sample_kernel(SampleArgs a) {
   extern __shared__ unsigned long long sort_keys[];   // [Q][SAMP_SORTN], only when top_p/top_k
   __shared__ long long s_tok[16];
   const int b = blockIdx.x;
@@ -80,6 +91,9 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
   pdl_launch_dependents();
   pdl_wait();
   if (a.reset_word && blockIdx.x == 0 && threadIdx.x == 0) *a.reset_word = 0;
+  const int log_step = (a.steplog && st && blockIdx.x == 0 && threadIdx.x == 0) ? min(st->steps, 4000) : -1;
+  if (log_step >= 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.steplog[8200 + 2 * log_step] = t; }
+#define SLOG(k) do { if (log_step >= 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); a.steplog[16400 + 8 * log_step + (k)] = t_; } } while (0)
 
   int offset_new = 0;
   uint64_t draw = a.draw_index;
@@ -155,16 +169,17 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
         }
       }
 #pragma unroll
-      for (int j = 0; j < SAMP_NPER; ++j) x[j] = (x[j] <= 0.0f) ? x[j] * f[j] : x[j] / f[j];
+      for (int j = 0; j < SAMP_NPER; ++j) x[j] = (f[j] == 1.0f) ? x[j] : ((x[j] <= 0.0f) ? x[j] * f[j] : x[j] / f[j]);   // x * 1 == x / 1 == x
     }
 
+    SLOG(0);
     int best = 0;
     if (a.sp.temperature > 0.0f) {
       // ---- softmax(logits / T) (sampling.py:217) ----
       float m = -INFINITY;
 #pragma unroll
       for (int j = 0; j < SAMP_NPER; ++j) {
-        x[j] = x[j] / a.sp.temperature;
+        if (a.sp.temperature != 1.0f) x[j] = x[j] / a.sp.temperature;           // x / 1 == x
         m = fmaxf(m, x[j]);
       }
       m = warp_max(m);
@@ -176,8 +191,9 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
       }
       s = warp_sum(s);
 #pragma unroll
-      for (int j = 0; j < SAMP_NPER; ++j) x[j] = x[j] / s;
+      for (int j = 0; j < SAMP_NPER; ++j) x[j] = div_pos(x[j], s);
 
+      SLOG(1);
       // ---- NovelAI unified (sampling.py:60-63) ----
       if (a.sp.linear > 0.0f) {
         float ent = 0.f;
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
         }
         s2 = warp_sum(s2);
 #pragma unroll
-        for (int j = 0; j < SAMP_NPER; ++j) x[j] = x[j] / s2;
+        for (int j = 0; j < SAMP_NPER; ++j) x[j] = div_pos(x[j], s2);
       }
 
       // ---- top-p / top-k need the row sorted (sampling.py:77-80,93-98) ----
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
           }
           s3 = warp_sum(s3);
 #pragma unroll
-          for (int j = 0; j < SAMP_NPER; ++j) x[j] = x[j] / s3;
+          for (int j = 0; j < SAMP_NPER; ++j) x[j] = div_pos(x[j], s3);
           __syncwarp();
           if (a.sp.top_k > 0) {
             // kept entries were all divided by s3 (order preserved), dropped ones are 0: the k-th largest of the
@@ -281,7 +297,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
             }
             s4 = warp_sum(s4);
 #pragma unroll
-            for (int j = 0; j < SAMP_NPER; ++j) x[j] = x[j] / s4;
+            for (int j = 0; j < SAMP_NPER; ++j) x[j] = div_pos(x[j], s4);
           }
         } else {
           int k = min(a.sp.top_k, V);
@@ -294,7 +310,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
           }
           s4 = warp_sum(s4);
 #pragma unroll
-          for (int j = 0; j < SAMP_NPER; ++j) x[j] = x[j] / s4;
+          for (int j = 0; j < SAMP_NPER; ++j) x[j] = div_pos(x[j], s4);
         }
       }
 
@@ -313,9 +329,10 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
         }
         s5 = warp_sum(s5);
 #pragma unroll
-        for (int j = 0; j < SAMP_NPER; ++j) x[j] = x[j] / s5;
+        for (int j = 0; j < SAMP_NPER; ++j) x[j] = div_pos(x[j], s5);
       }
 
+      SLOG(2);
       // ---- exponential race: argmax(p / q) (sampling.py:28-30) ----
       const float* qrow = nullptr;
       if (st && a.q_stream && draw < (uint64_t)a.q_calls)
@@ -324,12 +341,15 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
         qrow = a.q + ((size_t)b * Q + qi) * V;
       float bs = -INFINITY;
       int bi = 0x7fffffff;
+      uint4 rnd = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int j = 0; j < SAMP_NPER; ++j) {
         int i = j * 32 + lane;
+        if (!qrow && (j & 3) == 0) rnd = exp1_block(a.seed, draw, (uint32_t)(b * Q + qi), (uint32_t)(j >> 2), (uint32_t)lane);
         if (i < V) {
-          float qq = qrow ? qrow[i] : exp1_draw(a.seed, draw, (uint32_t)(b * Q + qi), (uint32_t)i);
-          float sc = x[j] / qq;
+          const uint32_t bits = (j & 3) == 0 ? rnd.x : ((j & 3) == 1 ? rnd.y : ((j & 3) == 2 ? rnd.z : rnd.w));
+          float qq = qrow ? qrow[i] : exp1_from_bits(bits);
+          float sc = div_pos(x[j], qq);
           if (sc > bs) { bs = sc; bi = i; }     // ascending i per lane: first max kept
         }
       }
@@ -357,6 +377,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
       }
       best = bi;
     }
+    SLOG(3);
     if (lane == 0) {
       s_tok[qi] = best;
       if (a.tokens) a.tokens[(size_t)b * Q + qi] = best;
@@ -364,6 +385,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
   }
   if (!st) return;
   __syncthreads();
+  SLOG(4);
 
   // ---- EOS state machine + frame write (lane k <-> codebook k of warp 0), then counters (lane 0) ----
   if (warp != 0) return;
@@ -391,8 +413,10 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
     if (!a.first) rem -= 1;                       // tensor_ops.py:87
     st->remaining[b] = rem;
     st->stopping[b] = stop;
+    SLOG(5);
     __threadfence();
     const int arrived = atomicAdd(&st->arrive, 1);
+    SLOG(6);
     if (arrived == a.B - 1) {                     // last utterance of this step closes the step
       st->arrive = 0;
       st->draw_idx += 1;
@@ -411,6 +435,7 @@ __global__ void __launch_bounds__(512, 1) sample_kernel(SampleArgs a) {
           if (all_done) { done = 1; steps = step_idx; }   // `break` precedes `step = step_idx + 1`
         }
         st->offset = offset_new; st->steps = steps; st->step_idx = step_idx + 1; st->done = done;
+        if (a.steplog) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.steplog[8200 + 2 * min(step_idx, 4000) + 1] = t; }
         // host-visible progress (host-mapped memory, PCIe write): only on the steps the host may look at
         if (a.mirror && (check || done)) { a.mirror[0] = offset_new; a.mirror[1] = step_idx + 1; a.mirror[3] = steps; a.mirror[2] = done; }
       }
@@ -428,19 +453,21 @@ zb_status zb_launch_sample(zb_ctx* ctx, const zb_sample_launch& L, cudaStream_t 
   a.q = L.q; a.seed = L.seed; a.draw_index = L.draw_index; a.sp = L.sp; a.apply_bias = L.apply_bias;
   a.tokens = L.tokens; a.st = L.st; a.delayed = L.delayed; a.T = L.T; a.ctx_len = L.ctx_len;
   a.lengths = L.lengths; a.q_stream = L.q_stream; a.q_calls = L.q_calls; a.logits_trace = L.logits_trace;
-  a.trace_calls = L.trace_calls; a.first = L.first; a.prefix_len = L.prefix_len; a.mirror = L.mirror; a.reset_word = L.reset_word;
+  a.trace_calls = L.trace_calls; a.first = L.first; a.prefix_len = L.prefix_len; a.mirror = L.mirror; a.reset_word = L.reset_word; a.steplog = zb_debug_steplog_ptr();
   ZB_REQUIRE(ctx, L.Q >= 1 && L.Q <= 16, "sampler: Q=%d unsupported (1..16)", L.Q);
   ZB_REQUIRE(ctx, L.V >= 2 && L.V <= SAMP_MAXV, "sampler: V=%d unsupported (<= %d)", L.V, SAMP_MAXV);
   ZB_REQUIRE(ctx, L.B >= 1, "sampler: B=%d", L.B);
   size_t smem = 0;
   if (L.sp.temperature > 0.f && (L.sp.top_p > 0.f || L.sp.top_k > 0)) smem = (size_t)L.Q * SAMP_SORTN * 8;
   ZB_REQUIRE(ctx, smem <= 227 * 1024, "sampler: top-p/top-k with Q=%d codebooks needs %zu bytes of shared memory", L.Q, smem);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    ZB_CUDA(ctx, cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+  static size_t attr[2] = {0, 0};
+  const int variant = L.Q <= 9 ? 0 : 1;
+  auto kernel = variant == 0 ? sample_kernel<288> : sample_kernel<512>;
+  if (smem > 48 * 1024 && smem > attr[variant]) {
+    ZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[variant] = smem;
   }
-  ZB_CUDA(ctx, zb_launch_pdl(sample_kernel, dim3(L.B), dim3(32 * L.Q), smem, stream, a));
+  ZB_CUDA(ctx, zb_launch_pdl(kernel, dim3(L.B), dim3(32 * L.Q), smem, stream, a));
   ctx->launches++;
   return ZB_OK;
 }

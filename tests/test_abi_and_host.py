@@ -122,3 +122,16 @@ def test_prefix_conditioner_matches_reference_golden():
     d = make_cond_dict(text="hi", speaker=torch.zeros(1, 1, 128), device="cpu")
     assert set(d) == {"espeak", "speaker", "emotion", "fmax", "pitch_std", "speaking_rate", "language_id", "ctc_loss", "speaker_noised"}
     assert d["language_id"].item() == 24 and abs(float(d["emotion"].sum()) - 1.0) < 1e-6
+
+
+def test_shipped_configs_load():
+    """configs/*.json (the hybrid one states the assumed shape) parse into ZonosConfig."""
+    import json
+    from zonos_b200.config import ZonosConfig, hybrid_config_dict, transformer_config_dict
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs")
+    hyb = json.load(open(os.path.join(root, "zonos_v0.1_hybrid.json")))
+    assert "ASSUMED" in hyb["_comment"]
+    c = ZonosConfig.from_dict(hyb)
+    assert c.backbone.n_layer == hybrid_config_dict()["backbone"]["n_layer"] and c.backbone.ssm_cfg == {"layer": "Mamba2"}
+    t = ZonosConfig.from_dict(json.load(open(os.path.join(root, "zonos_v0.1_transformer.json"))))
+    assert t.backbone.n_layer == 26 and t.backbone.attn_layer_idx == list(range(26))

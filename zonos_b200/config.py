@@ -60,7 +60,7 @@ class ZonosConfig:
 
     @classmethod
     def from_dict(cls, d: dict) -> "ZonosConfig":
-        d = dict(d)
+        d = {k: v for k, v in d.items() if not k.startswith("_")}          # "_comment" keys of the shipped configs/*.json
         backbone = BackboneConfig(**d.pop("backbone"))
         prefix = PrefixConditionerConfig(**d.pop("prefix_conditioner"))
         return cls(backbone, prefix, **d)

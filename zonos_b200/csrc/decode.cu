@@ -727,6 +727,10 @@ struct MegaArgs {
 };
 
 constexpr int kMegaStageBytes = 32 * 1024, kMegaAttnBytes = 40 * 1024;
+// consumer warps of the persistent kernel (+ 1 producer warp).  Nine warps leave 168 registers per thread (17 warps: 96,
+// with spills), and everything a warp does redundantly (norm statistics, index math, barrier and ring bookkeeping, the
+// per-stage reduction tree) is issued half as often: the warps share 4 issue slots.
+constexpr int kMW = 8;
 
 // ---- tagged activation words -----------------------------------------------------------------------------------
 // The phases of a step depend on each other all-to-all (every CTA needs the whole activation vector the previous
@@ -819,7 +823,7 @@ __device__ __forceinline__ void mega_produce(const GemvArgs& a, unsigned char* r
 // consumers: one matrix phase.  wait_full / release control the out_proj "hold" (first pass keeps the slots).
 template <int R, int NC, int RW, int PRO, int EPI>
 __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* ring, float* part, uint64_t* full_bar, uint64_t* empty_bar,
-                                             float (*red)[kW3][4], int S, int& gst, bool release, int warp, int lane,
+                                             float (*red)[kMW][4], int S, int& gst, bool release, int warp, int lane,
                                              const uint32_t* xt, uint32_t tag_in, uint32_t* yt, uint32_t tag_out, const uint32_t* rt, uint32_t* qt,
                                              uint32_t* kvt, unsigned long long* stamp, int norm_pending = 0, const MegaQkvPre* qkv_pre = nullptr, unsigned long long* dbg = nullptr) {
 #define DBG(i) do { if (dbg && threadIdx.x == 0) dbg[i] = gtime(); } while (0)
@@ -827,7 +831,7 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   constexpr int Kc = NC * 256;
   const int K = a.K, row_bytes = K * 2;
   const int KS = K / Kc;
-  const int RPS = (kW3 / KS) * RW;
+  const int RPS = (kMW / KS) * RW;
   int u_begin, nrows;
   mega_slice<EPI>(a, u_begin, nrows);
   const int nstage = (nrows + RPS - 1) / RPS;
@@ -869,7 +873,7 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
     DBG(1);
     if (norm_pending == 0) asm volatile("cp.async.wait_group 0;" ::: "memory"); else asm volatile("cp.async.wait_group 1;" ::: "memory");
     DBG(2);
-    asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
     DBG(3);
     // every warp sums the KS per-warp partials with a fixed shuffle tree (lane q holds slice q): far fewer issue
     // slots than a serial loop in each of the 16 warps, and the same bits in every warp
@@ -978,7 +982,7 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
     else { src += kMegaStageBytes; fb += 8; eb += 8; }
   }
   DBG(6);
-  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
   DBG(7);
 
   if (e_on) {
@@ -1049,7 +1053,7 @@ __device__ __forceinline__ void mega_attention_prefetch(const MegaArgs& m, const
   bf16* vs = ks + kCH * kKStride;
   const bf16* kp = kv_layer + (((size_t)t.page * 2 + 0) * m.Hkv + t.g) * kCH * kHD;
   const bf16* vp = kv_layer + (((size_t)t.page * 2 + 1) * m.Hkv + t.g) * kCH * kHD;
-  for (int c = threadIdx.x; c < kCH * kHD / 8; c += kW3 * 32) {
+  for (int c = threadIdx.x; c < kCH * kHD / 8; c += kMW * 32) {
     const int tok = c / (kHD / 8), d8 = (c % (kHD / 8)) * 8;
     if (tok < t.n_old) {
       cp_async16(ks + tok * kKStride + d8, kp + tok * kHD + d8);
@@ -1080,7 +1084,7 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
   // `prefetched`; this step's own token (index kv_len-1) is fetched now
   const int n_old = prefetched ? max(0, min(nk, kv_len - 1 - k0)) : 0;
   const int tok_new = kv_len - 1 - k0;                                  // this step's token, if it falls into this split
-  for (int c = threadIdx.x; c < kCH * kHD / 8; c += kW3 * 32) {
+  for (int c = threadIdx.x; c < kCH * kHD / 8; c += kMW * 32) {
     const int tok = c / (kHD / 8), d8 = (c % (kHD / 8)) * 8;
     if (tok >= n_old && tok < nk && tok != tok_new) {
       cp_async16(ks + tok * kKStride + d8, kp + tok * kHD + d8);
@@ -1095,8 +1099,9 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
   if (warp < G) {                                                       // q of this step: tagged words from the in_proj phase
     const uint4 qv = poll_v4(m.qt + (size_t)r * m.Hq * kHD + (size_t)head * kHD + lane * 4, tag_in);
     *reinterpret_cast<float4*>(&qs[warp * kHD + lane * 4]) = make_float4(untag(qv.x), untag(qv.y), untag(qv.z), untag(qv.w));
-  } else if (warp >= 8 && warp < 10 && tok_new >= 0 && tok_new < nk) {  // K (warp 8) and V (warp 9) of this step's token
-    const int kvsel = warp - 8;
+  }
+  if (warp >= kMW - 2 && tok_new >= 0 && tok_new < nk) {                // K and V of this step's token: the last two warps
+    const int kvsel = warp - (kMW - 2);
     const uint4 nv = poll_v4(m.kvt + ((size_t)r * 2 + kvsel) * m.Hkv * kHD + (size_t)g * kHD + lane * 4, tag_in);
     uint2 pk;
     pk.x = (nv.x >> 16) | (nv.y & 0xffff0000u);
@@ -1106,7 +1111,7 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
   }
   if (stamp && threadIdx.x == 0) *stamp = gtime();
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
   if (warp < G) {
     float sc[2];
 #pragma unroll
@@ -1141,7 +1146,7 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
     *reinterpret_cast<float4*>(part + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
     if (lane == 0) { part[kHD] = mx; part[kHD + 1] = l; }
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
   if (threadIdx.x == 0) {
     // one acq_rel RMW publishes this CTA's partials (cumulative over the CTA barrier) and acquires the others'
     int32_t* cnt = m.attn_counters + (size_t)r * m.Hkv + g;
@@ -1150,7 +1155,7 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
     *s_last = (prev == nact - 1);
     if (*s_last) *cnt = 0;
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
   if (*s_last && warp < G) {
     const float* base = m.attn_part + (((size_t)r * m.Hq + head) * m.nsplit) * kPart;
     // one pass with a running maximum (online softmax merge): the loads of all splits are independent, so the merge
@@ -1173,7 +1178,7 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
                                   tag_word(acc[3] * inv, tag_out));
     st_relaxed_v4(m.ayt + (size_t)r * m.Hq * kHD + (size_t)head * kHD + lane * 4, outv);
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(kW3 * 32) : "memory");       // scratch free for the next unit
+  asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");       // scratch free for the next unit
 }
 
 __device__ __forceinline__ void mega_fill(GemvArgs& a, const MegaArgs& m, int R) {
@@ -1184,10 +1189,10 @@ __device__ __forceinline__ void mega_fill(GemvArgs& a, const MegaArgs& m, int R)
 }
 
 template <int R>
-__global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __grid_constant__ MegaArgs m) {
+__global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __grid_constant__ MegaArgs m) {
   extern __shared__ __align__(128) unsigned char smem_m[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-  __shared__ float red[2][kW3][4];
+  __shared__ float red[2][kMW][4];
   if (loop_idle(m.loop, m.T_delayed)) return;                 // same answer in every CTA: the loop state only changes in the sampler
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = m.ring_stages;
@@ -1196,14 +1201,14 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   unsigned char* attn_scratch = smem_m + (size_t)S * kMegaStageBytes + m.part_bytes;
   bf16* nbuf = reinterpret_cast<bf16*>(attn_scratch + kMegaAttnBytes);   // [2 buffers][weight | bias][D]: norm parameters, copied a layer ahead
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kW3); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kMW); }
     mbar_fence_init();
   }
   __syncthreads();
   const int qn = m.Hq * m.hd, nqkv = (m.Hq + 2 * m.Hkv) * m.hd;
   GemvArgs a;
 
-  if (warp == kW3) {
+  if (warp == kMW) {
     // ===== producer: the whole step's weights, in consumption order =====
     const uint64_t pol = m.evict_first ? l2_evict_first_policy() : 0ull;
     int gst = 0;
@@ -1236,7 +1241,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   auto norm_prefetch = [&](int buf, const bf16* w, const bf16* b) {
     const int chunks = m.D / 8;
     bf16* dstw = nbuf + (size_t)buf * 2 * m.D;
-    for (int q = threadIdx.x; q < 2 * chunks; q += kW3 * 32) {
+    for (int q = threadIdx.x; q < 2 * chunks; q += kMW * 32) {
       const bf16* src = q < chunks ? w + q * 8 : (b ? b + (q - chunks) * 8 : nullptr);
       if (src) cp_async16(dstw + q * 8, src);
     }
@@ -1273,7 +1278,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   {
     const int d_begin = (int)((long long)blockIdx.x * m.D / gridDim.x), d_end = (int)((long long)(blockIdx.x + 1) * m.D / gridDim.x);
     const long long col = m.loop ? (long long)m.loop->offset : 0;
-    for (int t = threadIdx.x; t < (d_end - d_begin) * m.B; t += kW3 * 32) {
+    for (int t = threadIdx.x; t < (d_end - d_begin) * m.B; t += kMW * 32) {
       const int b = t / (d_end - d_begin), dd = d_begin + t % (d_end - d_begin);
       float acc = 0.f;
       for (int k = 0; k < m.Q; ++k) {
@@ -1297,7 +1302,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
     mega_attention_prefetch(m, L.kv_layer, ameta, attn_scratch);
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
-      mega_consume<R, 1, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
+      mega_consume<R, 2, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
                                                nullptr, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
     }
     MEGA_STAMP(); ++ph;
@@ -1322,11 +1327,11 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
         int g2 = gst0;
         unsigned long long* slot = MEGA_STAMP_SLOT();
         if (last) {
-          mega_consume<R, 1, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane, src, TAG(ph - 1), m.xt, TAG(ph),
+          mega_consume<R, 2, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane, src, TAG(ph - 1), m.xt, TAG(ph),
                                                      m.xt, nullptr, nullptr, slot);
         } else {
           uint32_t* dst = (src == m.y1t) ? m.ayt : m.y1t;
-          mega_consume<R, 1, 4, PRO_NONE, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, g2, false, warp, lane, src, TAG(ph - 1), dst, TAG(ph),
+          mega_consume<R, 2, 4, PRO_NONE, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, g2, false, warp, lane, src, TAG(ph - 1), dst, TAG(ph),
                                                      nullptr, nullptr, nullptr, slot);
           src = dst;
         }
@@ -1339,7 +1344,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
     a.W = L.fc1; a.N = 2 * m.F; a.K = m.D; a.ldx = m.D; a.nw = nbuf + 2 * m.D; a.nb = L.norm2_b ? nbuf + 3 * m.D : nullptr; a.ldy = m.F;
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
-      mega_consume<R, 1, 4, PRO_NORM, EPI_SILU>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
+      mega_consume<R, 2, 4, PRO_NORM, EPI_SILU>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
                                                 nullptr, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 220 : nullptr);
     }
     MEGA_STAMP(); ++ph;
@@ -1350,10 +1355,10 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       if (m.F == 8192)
-        mega_consume<R, 2, 2, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
+        mega_consume<R, 4, 2, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
                                                    m.xt, nullptr, nullptr, slot);
       else
-        mega_consume<R, 1, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
+        mega_consume<R, 2, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
                                                    m.xt, nullptr, nullptr, slot);
     }
     MEGA_STAMP(); ++ph;
@@ -1363,7 +1368,7 @@ __global__ void __launch_bounds__((kW3 + 1) * 32, 1) decode_step_kernel(const __
   a.W = m.heads; a.N = m.QV; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = m.normf_b ? nbuf + m.D : nullptr;
   {
     unsigned long long* slot = MEGA_STAMP_SLOT();
-    mega_consume<R, 1, 4, PRO_NORM, EPI_HEADS>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, 0u,
+    mega_consume<R, 2, 4, PRO_NORM, EPI_HEADS>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, 0u,
                                                nullptr, nullptr, nullptr, slot);
   }
   MEGA_STAMP();
@@ -1903,7 +1908,7 @@ zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cach
 bool zb_mega_supported(const zb_model* model, int R) {
   const zb_model_desc& d = model->d;
   static const int enabled = env_int("ZB_DECODE_MEGA", 1);
-  auto k_ok = [](int K) { return K == 256 || K == 512 || K == 1024 || K == 2048 || K == 4096; };
+  auto k_ok = [](int K) { return K == 512 || K == 1024 || K == 2048 || K == 4096; };   // 512 k per warp, 8 warps
   const int qn = d.n_heads * d.head_dim;
   if (model->n_mamba > 0) return false;                       // hybrid stacks use the multi-kernel graph path
   return enabled && R >= 2 && R <= 4 && d.head_dim == kHD && k_ok(d.d_model) && k_ok(qn) && (k_ok(d.d_ff) || d.d_ff == 8192) &&
@@ -1946,20 +1951,20 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
   const int grid = ctx->num_sms;
   // partial-sum buffer: the largest padded row count x k-slices over all matrices of the step
   auto part_need = [&](int nunits, bool pairs, int K, int NC, int RW) {
-    const int KS = K / (NC * 256), RPS = (kW3 / KS) * RW;
+    const int KS = K / (NC * 256), RPS = (kMW / KS) * RW;
     const int rows = ((nunits + grid - 1) / grid) * (pairs ? 2 : 1);
     return (size_t)((rows + RPS - 1) / RPS * RPS) * KS * R * sizeof(float);
   };
   const int qn = d.n_heads * d.head_dim;
-  size_t pb = part_need((d.n_heads + 2 * d.n_heads_kv) * d.head_dim / 2, true, d.d_model, 1, 4);
-  pb = std::max(pb, part_need(d.d_model, false, qn, 1, 4));
-  pb = std::max(pb, part_need(d.d_ff, true, d.d_model, 1, 4));
-  pb = std::max(pb, d.d_ff == 8192 ? part_need(d.d_model, false, d.d_ff, 2, 2) : part_need(d.d_model, false, d.d_ff, 1, 4));
-  pb = std::max(pb, part_need(m.QV, false, d.d_model, 1, 4));
+  size_t pb = part_need((d.n_heads + 2 * d.n_heads_kv) * d.head_dim / 2, true, d.d_model, 2, 4);
+  pb = std::max(pb, part_need(d.d_model, false, qn, 2, 4));
+  pb = std::max(pb, part_need(d.d_ff, true, d.d_model, 2, 4));
+  pb = std::max(pb, d.d_ff == 8192 ? part_need(d.d_model, false, d.d_ff, 4, 2) : part_need(d.d_model, false, d.d_ff, 2, 4));
+  pb = std::max(pb, part_need(m.QV, false, d.d_model, 2, 4));
   pb = (pb + 1023) / 1024 * 1024;
   {  // one epilogue item per consumer thread
     const int max_items = std::max(((d.d_ff + grid - 1) / grid) * R, ((m.QV + grid - 1) / grid) * R);
-    ZB_REQUIRE(ctx, max_items <= kW3 * 32 && ((d.d_model + grid - 1) / grid) * R <= kW3 * 32, "persistent decode: %d epilogue items per CTA", max_items);
+    ZB_REQUIRE(ctx, max_items <= kMW * 32 && ((d.d_model + grid - 1) / grid) * R <= kMW * 32, "persistent decode: %d epilogue items per CTA", max_items);
   }
   const size_t attn_bytes = kMegaAttnBytes + (size_t)4 * d.d_model * sizeof(bf16);   // attention tiles + two norm-parameter buffers
   const size_t avail = 227 * 1024 - 2048;
@@ -1971,13 +1976,14 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
   m.evict_first = evict_first;
   const size_t smem = (size_t)stages * kMegaStageBytes + pb + attn_bytes;
   auto launch = [&](auto kernel) -> zb_status {
-    static size_t attr = 0;
-    if (smem > attr) {
+    static size_t attr[2] = {0, 0};                      // per kernel instantiation (R <= 2, R <= 4): the generic lambda is ONE function for both
+    size_t& cur = attr[R <= 2 ? 0 : 1];
+    if (smem > cur) {
       ZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = smem;
+      cur = smem;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((kW3 + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((kMW + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;      // all CTAs must be co-resident: the phases meet at grid barriers
     at[0].val.cooperative = 1;

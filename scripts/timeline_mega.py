@@ -13,10 +13,10 @@ m = Zonos(ZonosConfig.from_dict(transformer_config_dict(**dims))).to(dev, torch.
 lib = C.CDLL(_lib.LIB_PATH); lib.zb_debug_timeline.argtypes = [C.c_void_p]
 B = int(os.environ.get("ZB_TL_B", "1"))
 cond = make_conditioning(2 * B, 160, 2048).to(dev)
-m.generate(cond, max_new_tokens=40, seed=1)
+m.generate(cond, max_new_tokens=40, batch_size=B, seed=1)
 buf = torch.zeros(512, dtype=torch.int64, device=dev)
 lib.zb_debug_timeline(C.c_void_p(buf.data_ptr()))
-m.generate(cond, max_new_tokens=400, seed=1)          # the buffer keeps the stamps of the LAST step (kv_len ~ 570)
+m.generate(cond, max_new_tokens=400, batch_size=B, seed=1)          # the buffer keeps the stamps of the LAST step (kv_len ~ 570)
 lib.zb_debug_timeline(C.c_void_p(0))
 t = buf.cpu().tolist()
 names = ["in_proj", "attn", "out1", "out2", "fc1", "fc2"]

@@ -1712,6 +1712,7 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
       if (tc) {
         if (zb_status st = norm_rows((const bf16*)L.norm_w, (const bf16*)L.norm_b)) return st;
         zb_gemm_tc g;
+        g.decode = (T == 1);
         g.W = (const bf16*)L.in_proj; g.x = s.xn; g.ldx = d.d_model; g.M = M; g.N = ipo; g.K = d.d_model; g.epi = 0; g.y = s.zx; g.ldy = ipo;
         if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
       } else {
@@ -1737,6 +1738,7 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
       ctx->launches++;
       if (tc && d.d_inner % 64 == 0) {
         zb_gemm_tc g;
+        g.decode = (T == 1);
         g.W = (const bf16*)L.out_proj; g.x = s.gn; g.ldx = d.d_inner; g.M = M; g.N = d.d_model; g.K = d.d_inner;
         g.epi = 1; g.y = x; g.ldy = d.d_model; g.resid = x; g.ldr = d.d_model;
         if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
@@ -1753,6 +1755,7 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
     if (tc_qkv) {
       if (zb_status st = norm_rows((const bf16*)L.norm_w, (const bf16*)L.norm_b)) return st;
       zb_gemm_tc g;
+      g.decode = (T == 1);
       g.W = (const bf16*)L.in_proj; g.x = s.xn; g.ldx = d.d_model; g.M = M; g.N = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim; g.K = d.d_model;
       g.epi = 2; g.T = T; g.Hq = d.n_heads; g.Hkv = d.n_heads_kv; g.hd = d.head_dim; g.rope_interleaved = d.rope_interleaved;
       g.rope = d.rope_table; g.rope_len = d.rope_len; g.lengths = cache->lengths; g.page_table = cache->page_table;
@@ -1788,6 +1791,7 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
       if (!last) ZB_REQUIRE(ctx, qn == d.d_model, "out_proj_repeats > 1 needs H*hd == D");
       if (tc) {
         zb_gemm_tc g;
+        g.decode = (T == 1);
         g.W = (const bf16*)L.out_proj; g.x = src; g.ldx = qn; g.M = M; g.N = d.d_model; g.K = qn;
         g.epi = last ? 1 : 0; g.y = dst; g.ldy = d.d_model; g.resid = x; g.ldr = d.d_model;
         if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
@@ -1808,10 +1812,12 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
     if (tc) {
       if (zb_status st = norm_rows((const bf16*)L.norm2_w, (const bf16*)L.norm2_b)) return st;
       zb_gemm_tc g;
+      g.decode = (T == 1);
       g.W = (const bf16*)L.fc1; g.x = s.xn; g.ldx = d.d_model; g.M = M; g.N = 2 * d.d_ff; g.K = d.d_model; g.F = d.d_ff;
       g.epi = 3; g.y = s.h; g.ldy = d.d_ff;
       if (zb_status st = zb_launch_gemm_tc(ctx, g, stream)) return st;
       zb_gemm_tc g2;
+      g2.decode = (T == 1);
       g2.W = (const bf16*)L.fc2; g2.x = s.h; g2.ldx = d.d_ff; g2.M = M; g2.N = d.d_model; g2.K = d.d_ff;
       g2.epi = 1; g2.y = x; g2.ldy = d.d_model; g2.resid = x; g2.ldr = d.d_model;
       if (zb_status st = zb_launch_gemm_tc(ctx, g2, stream)) return st;

@@ -322,7 +322,11 @@ zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t strea
   const int ntiles = (g.epi == TEPI_SILU) ? (g.F + 63) / 64 : (g.N + TC_BM - 1) / TC_BM;
   // split-K for the bandwidth-bound small-M regime: enough CTAs to pull weights with every SM
   int ksplit = 1;
-  static const int splitk_on = getenv("ZB_TC_SPLITK") ? atoi(getenv("ZB_TC_SPLITK")) : 0;   // measured slower on B200 (B=64 decode: 1.75 s vs 1.52 s per pass): off by default
+  // ZB_TC_SPLITK: 0 never, 1 whenever the grid is smaller than the GPU, default -1 = only for few activation rows and
+  // few weight tiles (batch 3..8 decode: the N=2048 matrices are 16 tiles, i.e. 16 SMs would stream them alone; at
+  // batch 64 split-K measured slower: 1.75 s vs 1.52 s per pass)
+  static const int splitk_env = getenv("ZB_TC_SPLITK") ? atoi(getenv("ZB_TC_SPLITK")) : -1;
+  const bool splitk_on = splitk_env > 0 || (splitk_env < 0 && g.decode && g.M <= 32 && ntiles <= 48);
   if (splitk_on && mtiles == 1 && ntiles < ctx->num_sms) {
     ksplit = (ctx->num_sms + ntiles - 1) / ntiles;
     const int nkb = g.K / TC_BK;

@@ -80,6 +80,7 @@ struct zb_gemm_tc {
   int T = 1, Hq = 0, Hkv = 0, hd = 0, rope_interleaved = 1, rope_len = 0, max_pages = 0;
   const float* rope = nullptr; const int32_t* lengths = nullptr; const int32_t* page_table = nullptr; bf16* kv_layer = nullptr; bf16* q_out = nullptr;
   int B = 0; float cfg_scale = 1.0f; float* logits = nullptr; int QV = 0;
+  bool decode = false;         // one token per row: split-K allowed (never in prefill, whose results must not depend on the batch size)
 };
 zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t stream);
 

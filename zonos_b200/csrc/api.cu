@@ -208,7 +208,7 @@ __global__ void init_state_kernel(zb_loop_state* st, int B, int offset, int max_
   if (threadIdx.x == 0) {
     st->offset = offset; st->step_idx = 0; st->done = 0; st->steps = 0; st->draw_idx = 0; st->arrive = 0; st->max_steps = max_steps;
   }
-  for (int b = threadIdx.x; b < B; b += blockDim.x) { st->remaining[b] = max_steps; st->stopping[b] = 0; }
+  for (int b = threadIdx.x; b < B; b += blockDim.x) { st->remaining[b] = max_steps; st->stopping[b] = 0; st->row_arrive[b] = 0; }
 }
 
 zb_status enqueue_step(zb_gen* g, cudaStream_t s) {

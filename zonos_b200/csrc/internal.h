@@ -15,6 +15,8 @@ struct zb_loop_state {
   int32_t _pad;
   long long remaining[ZB_MAX_B];
   int32_t stopping[ZB_MAX_B];
+  int32_t row_arrive[ZB_MAX_B];        // wide sampler: codebook rows of an utterance that have their token (one CTA per row)
+  long long tok[ZB_MAX_B * 16];        // wide sampler: the tokens of the current step, [utterance][codebook]
 };
 
 struct zb_model {

@@ -78,6 +78,67 @@ struct SampleArgs {
   unsigned long long* steplog; // debug: [8200 + 2*step] start (after the dependency wait), +1 end (zb_debug_steplog)
 };
 
+// EOS state machine + frame write (lane k <-> codebook k), then counters (lane 0): run by ONE warp per utterance once all
+// of its Q tokens are in s_tok
+__device__ __forceinline__ void sample_close_row(const SampleArgs& a, zb_loop_state* st, int b, const volatile long long* s_tok, int offset_new,
+                                                 int lane, int log_step) {
+  const int V = a.V, Q = a.Q;
+#define SLOG(k) do { if (log_step >= 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); a.steplog[16400 + 8 * log_step + (k)] = t_; } } while (0)
+  const int eos = V - 1, mask_tok = V;           // 1024 / 1025
+  long long rem = st->remaining[b];
+  int stop = st->stopping[b];
+  if (!a.first && s_tok[0] == eos) {             // model.py:483-488
+    rem = min(rem, (long long)Q);
+    stop = 1;
+  }
+  if (lane < Q) {
+    long long tok = s_tok[lane];
+    if (!a.first && stop) {                      // tensor_ops.py:193-211
+      const long long eos_idx = min((long long)Q - rem, (long long)(Q - 1));   // model.py:490-491
+      if (lane < eos_idx) tok = mask_tok;
+      else if (lane == eos_idx) tok = eos;
+    }
+    int64_t* cell = a.delayed + ((size_t)b * Q + lane) * a.T + offset_new;    // tensor_ops.py:42-53 (only where == -1)
+    if (*cell == -1) *cell = tok;
+  }
+  if (lane == 0) {
+    const int adv = a.first ? a.prefix_len : 1;  // model.py:430-431 / tensor_ops.py:85-86
+    a.lengths[b] += adv;
+    a.lengths[a.B + b] += adv;
+    if (!a.first) rem -= 1;                       // tensor_ops.py:87
+    st->remaining[b] = rem;
+    st->stopping[b] = stop;
+    SLOG(5);
+    __threadfence();
+    const int arrived = atomicAdd(&st->arrive, 1);
+    SLOG(6);
+    if (arrived == a.B - 1) {                     // last utterance of this step closes the step
+      st->arrive = 0;
+      st->draw_idx += 1;
+      if (!a.first) {
+        const int step_idx = st->step_idx;
+        int done = 0, steps = step_idx + 1;       // model.py:506
+        bool check = (step_idx % 16 == 15);       // tensor_ops.py:90-103
+        if (!check && (step_idx % 8 == 7)) {
+          int est = a.B * 10 - (step_idx + 1);    // cpu_step_counter == step_idx + 1
+          if (est < 0) est = 0;
+          check = est < 5;
+        }
+        if (check) {
+          bool all_done = true;
+          for (int bb = 0; bb < a.B; ++bb) all_done = all_done && (((volatile long long*)st->remaining)[bb] <= 0);
+          if (all_done) { done = 1; steps = step_idx; }   // `break` precedes `step = step_idx + 1`
+        }
+        st->offset = offset_new; st->steps = steps; st->step_idx = step_idx + 1; st->done = done;
+        if (a.steplog) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.steplog[8200 + 2 * min(step_idx, 4000) + 1] = t; }
+        // host-visible progress (host-mapped memory, PCIe write): only on the steps the host may look at
+        if (a.mirror && (check || done)) { a.mirror[0] = offset_new; a.mirror[1] = step_idx + 1; a.mirror[3] = steps; a.mirror[2] = done; }
+      }
+    }
+  }
+}
+#undef SLOG
+
 // kThreads = 32 * (most codebooks the launch may have): 288 for the 9 codebooks of Zonos leaves 224 registers per thread
 // (the row lives in registers: 33 values per lane plus temporaries - 128 registers spill)
 template <int kThreads>
@@ -389,58 +450,253 @@ __global__ void __launch_bounds__(kThreads, 1) sample_kernel(SampleArgs a) {
 
   // ---- EOS state machine + frame write (lane k <-> codebook k of warp 0), then counters (lane 0) ----
   if (warp != 0) return;
-  const int eos = V - 1, mask_tok = V;           // 1024 / 1025
-  long long rem = st->remaining[b];
-  int stop = st->stopping[b];
-  if (!a.first && s_tok[0] == eos) {             // model.py:483-488
-    rem = min(rem, (long long)Q);
-    stop = 1;
-  }
-  if (lane < Q) {
-    long long tok = s_tok[lane];
-    if (!a.first && stop) {                      // tensor_ops.py:193-211
-      const long long eos_idx = min((long long)Q - rem, (long long)(Q - 1));   // model.py:490-491
-      if (lane < eos_idx) tok = mask_tok;
-      else if (lane == eos_idx) tok = eos;
+  sample_close_row(a, st, b, s_tok, offset_new, lane, log_step);
+}
+
+
+// ---- wide variant: grid (B, Q), 128 threads per codebook row ------------------------------------------------------
+// One warp per row is a serial chain of ~12 k instructions (IEEE divisions, precise exp/log in the reference's op order):
+// 21 us per step whether the 9 warps share an SM or not.  Four warps per row and one CTA per row cut the chain to 9
+// elements per thread.  Same stages and op order per element; sums are reduced thread -> warp (butterfly) -> the 4
+// warps in order.  Used when no sort is needed (top_p = top_k = 0); the Exp(1) draw of an element is the same Philox
+// word as in sample_kernel.
+#define SAMPW_THREADS 128
+#define SAMPW_NPER 9          // ceil(1056 / 128)
+__device__ __forceinline__ float blockw_sum(float v, float* red, int warp, int lane) {
+  v = warp_sum(v);
+  __syncthreads();                                  // red is free again
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  return ((red[0] + red[1]) + red[2]) + red[3];
+}
+__device__ __forceinline__ float blockw_max(float v, float* red, int warp, int lane) {
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+}
+
+__global__ void __launch_bounds__(SAMPW_THREADS) sample_wide_kernel(SampleArgs a) {
+  __shared__ float red[4];
+  __shared__ float red_s[4];
+  __shared__ int red_i[4];
+  __shared__ int s_last;
+  const int b = blockIdx.x, qi = blockIdx.y;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int V = a.V, Q = a.Q;
+  zb_loop_state* st = a.st;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int log_step = (a.steplog && st && b == 0 && qi == 0 && t == 0) ? min(st->steps, 4000) : -1;
+  if (log_step >= 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); a.steplog[8200 + 2 * log_step] = t_; }
+
+  int offset_new = 0;
+  uint64_t draw = a.draw_index;
+  if (st) {
+    if (st->done) return;                                                   // liveness: model.py:468-472
+    offset_new = a.first ? st->offset : st->offset + 1;
+    if (!a.first && offset_new >= a.T) {
+      if (b == 0 && qi == 0 && t == 0) {
+        st->offset = offset_new; st->done = 1;
+        if (a.mirror) { a.mirror[0] = offset_new; a.mirror[2] = 1; }
+      }
+      return;
     }
-    int64_t* cell = a.delayed + ((size_t)b * Q + lane) * a.T + offset_new;    // tensor_ops.py:42-53 (only where == -1)
-    if (*cell == -1) *cell = tok;
+    draw = (uint64_t)st->draw_idx;
   }
-  if (lane == 0) {
-    const int adv = a.first ? a.prefix_len : 1;  // model.py:430-431 / tensor_ops.py:85-86
-    a.lengths[b] += adv;
-    a.lengths[a.B + b] += adv;
-    if (!a.first) rem -= 1;                       // tensor_ops.py:87
-    st->remaining[b] = rem;
-    st->stopping[b] = stop;
-    SLOG(5);
-    __threadfence();
-    const int arrived = atomicAdd(&st->arrive, 1);
-    SLOG(6);
-    if (arrived == a.B - 1) {                     // last utterance of this step closes the step
-      st->arrive = 0;
-      st->draw_idx += 1;
-      if (!a.first) {
-        const int step_idx = st->step_idx;
-        int done = 0, steps = step_idx + 1;       // model.py:506
-        bool check = (step_idx % 16 == 15);       // tensor_ops.py:90-103
-        if (!check && (step_idx % 8 == 7)) {
-          int est = a.B * 10 - (step_idx + 1);    // cpu_step_counter == step_idx + 1
-          if (est < 0) est = 0;
-          check = est < 5;
+
+  const float* lrow = a.logits + ((size_t)b * Q + qi) * V;
+  float x[SAMPW_NPER];
+#pragma unroll
+  for (int j = 0; j < SAMPW_NPER; ++j) {
+    const int i = j * SAMPW_THREADS + t;
+    x[j] = (i < V) ? lrow[i] : -INFINITY;
+  }
+  if (a.apply_bias) {                                                       // model.py:433-437,476: EOS = V-1
+    const int eos = V - 1;
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j)
+      if (j * SAMPW_THREADS + t == eos) x[j] = (qi == 0) ? (x[j] - 0.69314718055994530942f) : -INFINITY;
+  }
+  if (st && a.logits_trace && draw < (uint64_t)a.trace_calls) {
+    float* tr = a.logits_trace + (((size_t)draw * a.B + b) * Q + qi) * V;
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j) {
+      const int i = j * SAMPW_THREADS + t;
+      if (i < V) tr[i] = x[j];
+    }
+  }
+  // ---- repetition penalty (sampling.py:159-163) ----
+  const int64_t* wtok = nullptr;
+  int wcount = 0;
+  if (st) {
+    if (!a.first) {
+      const int avail = min(offset_new, a.ctx_len);
+      wcount = min(a.sp.repetition_penalty_window, avail);
+      wtok = a.delayed + ((size_t)b * Q + qi) * a.T + (offset_new - wcount);
+    }
+  } else if (a.window) {
+    wcount = min(a.sp.repetition_penalty_window, a.W);
+    wtok = a.window + b * a.wsb + qi * a.wsq + (a.W - wcount);
+  }
+  if (wtok && a.sp.repetition_penalty != 1.0f && wcount > 0) {
+    float f[SAMPW_NPER];
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j) f[j] = 1.0f;
+    for (int w = 0; w < wcount; ++w) {
+      const long long tk = wtok[w];
+      int idx = (int)min(tk, (long long)(V - 1));
+      if (idx < 0) idx += V;
+#pragma unroll
+      for (int j = 0; j < SAMPW_NPER; ++j)
+        if (j * SAMPW_THREADS + t == idx) f[j] *= a.sp.repetition_penalty;
+    }
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j) x[j] = (f[j] == 1.0f) ? x[j] : ((x[j] <= 0.0f) ? x[j] * f[j] : x[j] / f[j]);
+  }
+
+  int best = 0;
+  if (a.sp.temperature > 0.0f) {
+    // ---- softmax(logits / T) (sampling.py:217) ----
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j) {
+      if (a.sp.temperature != 1.0f) x[j] = x[j] / a.sp.temperature;
+      m = fmaxf(m, x[j]);
+    }
+    m = blockw_max(m, red, warp, lane);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j) {
+      x[j] = expf(x[j] - m);
+      sum += x[j];
+    }
+    sum = blockw_sum(sum, red, warp, lane);
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j) x[j] = div_pos(x[j], sum);
+
+    // ---- NovelAI unified (sampling.py:60-63) ----
+    if (a.sp.linear > 0.0f) {
+      float ent = 0.f;
+      float lp[SAMPW_NPER];
+#pragma unroll
+      for (int j = 0; j < SAMPW_NPER; ++j) {
+        lp[j] = logf(fmaxf(x[j], 1e-20f));
+        ent += x[j] * lp[j];
+      }
+      ent = -blockw_sum(ent, red, warp, lane);
+      const float lin = __fadd_rn(a.sp.linear, __fmul_rn(ent, a.sp.conf));
+      float m2 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < SAMPW_NPER; ++j) {
+        const int i = j * SAMPW_THREADS + t;
+        const float raw = __fsub_rn(__fmul_rn(lp[j], lin), __fmul_rn(__fmul_rn(lp[j], lp[j]), a.sp.quad));
+        x[j] = (i < V) ? raw : -INFINITY;
+        m2 = fmaxf(m2, x[j]);
+      }
+      m2 = blockw_max(m2, red, warp, lane);
+      float s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < SAMPW_NPER; ++j) {
+        x[j] = expf(x[j] - m2);
+        s2 += x[j];
+      }
+      s2 = blockw_sum(s2, red, warp, lane);
+#pragma unroll
+      for (int j = 0; j < SAMPW_NPER; ++j) x[j] = div_pos(x[j], s2);
+    }
+
+    // ---- min-p (sampling.py:123-126) ----
+    if (a.sp.min_p > 0.0f) {
+      float pm = 0.f;
+#pragma unroll
+      for (int j = 0; j < SAMPW_NPER; ++j) pm = fmaxf(pm, x[j]);
+      pm = blockw_max(pm, red, warp, lane);
+      const float thr = a.sp.min_p * pm;
+      float s5 = 0.f;
+#pragma unroll
+      for (int j = 0; j < SAMPW_NPER; ++j) {
+        if (x[j] < thr) x[j] = 0.f;
+        s5 += x[j];
+      }
+      s5 = blockw_sum(s5, red, warp, lane);
+#pragma unroll
+      for (int j = 0; j < SAMPW_NPER; ++j) x[j] = div_pos(x[j], s5);
+    }
+
+    // ---- exponential race: argmax(p / q) (sampling.py:28-30) ----
+    const float* qrow = nullptr;
+    if (st && a.q_stream && draw < (uint64_t)a.q_calls)
+      qrow = a.q_stream + (((size_t)draw * a.B + b) * Q + qi) * V;
+    else if (!st && a.q)
+      qrow = a.q + ((size_t)b * Q + qi) * V;
+    float bs = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j) {
+      const int i = j * SAMPW_THREADS + t;
+      if (i < V) {
+        float qq;
+        if (qrow) qq = qrow[i];
+        else {
+          // element i of sample_kernel is (j32 = i / 32, lane): word j32 % 4 of the Philox block (j32 / 4, lane) = (j, lane), word = warp
+          const uint4 rnd = exp1_block(a.seed, draw, (uint32_t)(b * Q + qi), (uint32_t)j, (uint32_t)lane);
+          qq = exp1_from_bits(warp == 0 ? rnd.x : (warp == 1 ? rnd.y : (warp == 2 ? rnd.z : rnd.w)));
         }
-        if (check) {
-          bool all_done = true;
-          for (int bb = 0; bb < a.B; ++bb) all_done = all_done && (((volatile long long*)st->remaining)[bb] <= 0);
-          if (all_done) { done = 1; steps = step_idx; }   // `break` precedes `step = step_idx + 1`
-        }
-        st->offset = offset_new; st->steps = steps; st->step_idx = step_idx + 1; st->done = done;
-        if (a.steplog) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.steplog[8200 + 2 * min(step_idx, 4000) + 1] = t; }
-        // host-visible progress (host-mapped memory, PCIe write): only on the steps the host may look at
-        if (a.mirror && (check || done)) { a.mirror[0] = offset_new; a.mirror[1] = step_idx + 1; a.mirror[3] = steps; a.mirror[2] = done; }
+        const float sc = div_pos(x[j], qq);
+        if (sc > bs) { bs = sc; bi = i; }       // ascending i per thread: first max kept
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    if (lane == 0) { red_s[warp] = bs; red_i[warp] = bi; }
+    __syncthreads();
+    bs = red_s[0]; bi = red_i[0];
+#pragma unroll
+    for (int w = 1; w < 4; ++w)
+      if (red_s[w] > bs || (red_s[w] == bs && red_i[w] < bi)) { bs = red_s[w]; bi = red_i[w]; }
+    best = bi;
+  } else {
+    // greedy (sampling.py:229): argmax of the penalised logits, lowest index on ties
+    float bs = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < SAMPW_NPER; ++j) {
+      const int i = j * SAMPW_THREADS + t;
+      if (i < V && (x[j] > bs || bi == 0x7fffffff)) { bs = x[j]; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+    }
+    if (lane == 0) { red_s[warp] = bs; red_i[warp] = bi; }
+    __syncthreads();
+    bs = red_s[0]; bi = red_i[0];
+#pragma unroll
+    for (int w = 1; w < 4; ++w)
+      if (red_s[w] > bs || (red_s[w] == bs && red_i[w] < bi)) { bs = red_s[w]; bi = red_i[w]; }
+    best = bi;
   }
+  if (t == 0 && a.tokens) a.tokens[(size_t)b * Q + qi] = best;
+  if (!st) return;
+  // publish the token; the last row of the utterance to arrive carries on with the utterance's bookkeeping
+  if (t == 0) {
+    st->tok[b * 16 + qi] = best;
+    __threadfence();
+    const int last = atomicAdd(&st->row_arrive[b], 1) == Q - 1;
+    if (last) { st->row_arrive[b] = 0; __threadfence(); }
+    s_last = last;
+  }
+  __syncthreads();
+  if (!s_last || warp != 0) return;
+  sample_close_row(a, st, b, st->tok + b * 16, offset_new, lane, log_step);
 }
 
 }  // namespace
@@ -466,6 +722,12 @@ zb_status zb_launch_sample(zb_ctx* ctx, const zb_sample_launch& L, cudaStream_t 
   if (smem > 48 * 1024 && smem > attr[variant]) {
     ZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[variant] = smem;
+  }
+  static const int wide = getenv("ZB_SAMPLER_WIDE") ? atoi(getenv("ZB_SAMPLER_WIDE")) : 1;
+  if (wide && smem == 0 && L.V <= SAMPW_NPER * SAMPW_THREADS && L.B <= ZB_MAX_B) {     // no sort needed: one CTA of 4 warps per codebook row
+    ZB_CUDA(ctx, zb_launch_pdl(sample_wide_kernel, dim3(L.B, L.Q), dim3(SAMPW_THREADS), 0, stream, a));
+    ctx->launches++;
+    return ZB_OK;
   }
   ZB_CUDA(ctx, zb_launch_pdl(kernel, dim3(L.B), dim3(32 * L.Q), smem, stream, a));
   ctx->launches++;

@@ -16,7 +16,7 @@ cond = make_conditioning(2 * B, 160, 2048).to(dev)
 m.generate(cond, max_new_tokens=40, batch_size=B, seed=1)
 buf = torch.zeros(512, dtype=torch.int64, device=dev)
 lib.zb_debug_timeline(C.c_void_p(buf.data_ptr()))
-m.generate(cond, max_new_tokens=400, batch_size=B, seed=1)          # the buffer keeps the stamps of the LAST step (kv_len ~ 570)
+m.generate(cond, max_new_tokens=int(os.environ.get("ZB_TL_N", "400")), batch_size=B, seed=1)   # the buffer keeps the stamps of the LAST step (kv_len ~ 170 + N)
 lib.zb_debug_timeline(C.c_void_p(0))
 t = buf.cpu().tolist()
 names = ["in_proj", "attn", "out1", "out2", "fc1", "fc2"]

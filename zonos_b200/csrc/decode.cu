@@ -697,10 +697,10 @@ __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
 
 // ================================================================================================================
 // Persistent decode step: ONE cooperative launch runs embed -> 26 x (in_proj, attention, out_proj x2, fc1, fc2) ->
-// heads for up to 4 activation rows.  148 CTAs (one per SM) stay resident; the phases are separated by grid-wide
-// barriers (consumer warps only), while the producer warp of every CTA streams that CTA's slice of ALL the step's
-// weight matrices back to back through the shared-memory ring - weights do not depend on activations, so HBM keeps
-// streaming across phase boundaries and barrier/LayerNorm latency is hidden behind the ring.
+// heads for up to 4 activation rows.  148 CTAs (one per SM) stay resident.  The producer warp of every CTA streams that
+// CTA's slice of ALL the step's weight matrices back to back through the shared-memory ring - weights do not depend on
+// activations, so HBM keeps streaming across phase boundaries.  The 8 consumer warps run the phases; a phase starts as
+// soon as the tagged activation words of the previous one have arrived (no grid barrier, see "tagged activation words").
 // out_proj is applied twice by the reference (_torch.py:419-420): its slice is held in the ring between the two
 // passes, so it is read from HBM once.
 // ================================================================================================================
@@ -1991,7 +1991,7 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3((kMW + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;      // all CTAs must be co-resident: the phases meet at grid barriers
+    at[0].id = cudaLaunchAttributeCooperative;      // all CTAs must be co-resident: every phase spins on words the other CTAs write
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     ZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, m));

@@ -196,6 +196,7 @@ struct zb_gen {
   unsigned* mega_bar = nullptr;     // sync words of the persistent kernel ([1] = epoch of the tagged arena)
   uint32_t* mega_arena = nullptr;   // tagged activation words exchanged between its CTAs
   bool mega = false;
+  bool tc = false;                  // persistent tcgen05 decode step (decode_tc.cu); mega_layers / mega_bar / mega_arena then hold its table / barrier / arena
   int slab = -1;                    // index into ctx->gen_slabs
   cudaGraphExec_t graph = nullptr;
   int64_t launches_per_step = 0;
@@ -218,7 +219,11 @@ zb_status enqueue_step(zb_gen* g, cudaStream_t s) {
   zb_embed_launch E;
   E.model = g->model; E.codes = g->d.delayed; E.sb = (int64_t)g->d.Q * g->d.T_delayed; E.sq = g->d.T_delayed; E.st = 1;
   E.B = B; E.T = 1; E.repeat = 2; E.out = g->xdec; E.out_rs = md.d_model; E.loop = g->st; E.T_delayed = g->d.T_delayed;
-  if (g->mega) {
+  if (g->tc) {
+    // one cooperative launch: embed + all layers + heads, tcgen05 consumer
+    if (zb_status st = zb_launch_decode_tc(ctx, g->model, &g->cache, g->mega_layers, g->mega_bar, g->mega_arena, R, g->d.cfg_scale, g->logits, g->d.delayed,
+                                           g->d.T_delayed, g->st, s)) return st;
+  } else if (g->mega) {
     // one cooperative launch: embed + all layers + heads
     if (zb_status st = zb_launch_decode_step(ctx, g->model, &g->cache, g->mega_layers, g->mega_bar, g->mega_arena, R, g->max_kv, g->d.cfg_scale, g->logits,
                                              g->d.delayed, g->d.T_delayed, g->st, s)) return st;
@@ -264,11 +269,14 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
 #define G_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { zb_fail(ctx, ZB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); return fail(ZB_ERR_CUDA); } } while (0)
   // one slab per session (reused across sessions, see zb_gen_slab): loop state | logits | decode residual | layer
   // table | sync words | tagged activation arena
-  g->mega = zb_mega_supported(model, R);
+  g->tc = zb_tc_supported(model, R);
+  g->mega = g->tc || zb_mega_supported(model, R);           // both persistent paths: no CUDA graph, session table + arena in the slab
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t table_bytes = !g->mega ? 0 : g->tc ? zb_tc_table_bytes(model) : zb_mega_layers_bytes(model);
+  const size_t arena_bytes = !g->mega ? 0 : g->tc ? zb_tc_arena_bytes(model, R) : zb_mega_arena_bytes(model, R);
   const size_t o_st = 0, o_logits = o_st + up(sizeof(zb_loop_state)), o_x = o_logits + up((size_t)B * Q * md.head_vocab * 4);
-  const size_t o_layers = o_x + up((size_t)R * md.d_model * 2), o_bar = o_layers + up(g->mega ? zb_mega_layers_bytes(model) : 0);
-  const size_t o_arena = o_bar + 256, slab_need = o_arena + up(g->mega ? zb_mega_arena_bytes(model, R) : 0);
+  const size_t o_layers = o_x + up((size_t)R * md.d_model * 2), o_bar = o_layers + up(table_bytes);
+  const size_t o_arena = o_bar + 256, slab_need = o_arena + up(arena_bytes);
   {
     int pick = -1;
     for (size_t i = 0; i < ctx->gen_slabs.size(); ++i)
@@ -294,15 +302,15 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
     g->st_host[0] = desc->prefix_audio_len + 1;
     if (g->mega) {
       g->mega_layers = base + o_layers; g->mega_bar = (unsigned*)(base + o_bar); g->mega_arena = (uint32_t*)(base + o_arena);
-      std::vector<unsigned char> hb(zb_mega_layers_bytes(model));
-      if (zb_status st = zb_mega_layers_build(ctx, model, cache, hb.data())) return fail(st);
+      std::vector<unsigned char> hb(table_bytes);
+      if (zb_status st = g->tc ? zb_tc_table_build(ctx, model, cache, R, g->mega_arena, hb.data()) : zb_mega_layers_build(ctx, model, cache, hb.data())) return fail(st);
       if (sl.layers != hb || sl.layers_off != o_layers) {  // same model and cache as the slab's last session: already there
         sl.layers = hb; sl.layers_off = o_layers;
         G_CUDA(cudaMemcpyAsync(g->mega_layers, sl.layers.data(), hb.size(), cudaMemcpyHostToDevice, s));
         G_CUDA(cudaStreamSynchronize(s));                 // pageable source: keep the copy simple and finished
       }
       G_CUDA(cudaMemsetAsync(g->mega_bar, 0, 256, s));
-      G_CUDA(cudaMemsetAsync(g->mega_arena, 0, zb_mega_arena_bytes(model, R), s));   // tag 0 = never written
+      G_CUDA(cudaMemsetAsync(g->mega_arena, 0, arena_bytes, s));   // tag 0 = never written (decode.cu) / arrival counters (decode_tc.cu)
     }
   }
   const int offset0 = P + 1;

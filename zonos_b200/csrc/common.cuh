@@ -42,6 +42,7 @@ struct zb_ctx {
   int32_t* counters = nullptr;  // zeroed int32 words for last-CTA-done patterns
   cudaStream_t capture_stream = nullptr;   // graph capture happens here (the caller's stream may be the legacy one)
   std::vector<zb_gen_slab> gen_slabs;      // session memory, reused across generate calls
+  size_t max_dyn_smem_tc = 0;              // cudaFuncAttributeMaxDynamicSharedMemorySize set on this device for decode_tc_kernel
 };
 
 extern thread_local std::string g_zb_create_error;

@@ -73,6 +73,14 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
                                 uint32_t* arena, int R, int max_kv_len, float cfg_scale, float* logits, const int64_t* delayed, int T_delayed,
                                 const zb_loop_state* loop, cudaStream_t stream);
 
+// persistent decode step with a tcgen05 consumer, R = 2..128 rows (decode_tc.cu)
+bool zb_tc_supported(const zb_model* model, int R);
+size_t zb_tc_table_bytes(const zb_model* model);              // per-layer tensor maps + pointers (host-built, uploaded once per session)
+size_t zb_tc_arena_bytes(const zb_model* model, int R);       // activation / partial buffers of one generate session
+zb_status zb_tc_table_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, int R, void* arena_dev, void* host_buf);
+zb_status zb_launch_decode_tc(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const void* table_dev, unsigned* bar, void* arena, int R,
+                              float cfg_scale, float* logits, const int64_t* delayed, int T_delayed, const zb_loop_state* loop, cudaStream_t stream);
+
 // ---- tcgen05 GEMM (gemm_tc.cu): Y[M,N] = X[M,K] W[N,K]^T with fused epilogue ----
 struct zb_gemm_tc {
   const bf16* W = nullptr; const bf16* x = nullptr; long long ldx = 0; int M = 0, N = 0, K = 0;

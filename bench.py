@@ -7,8 +7,13 @@ Workload at N=1 GPU = BASELINE.json configs[1]: Zonos-v0.1-transformer, bf16, ba
 synthetic conditioning tokens.  With --gpus N every rank runs the same per-GPU workload on its own utterances
 (request sharding, no collective on the data path) => "scaling": "weak".
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--frames F] [--cond-len Lc]
-  python bench.py --impl reference ...      # the CPU oracle port of the reference path, timed on host cores
+The default run measures BOTH halves of BASELINE.json's metric: the headline fields are batch 1 (configs[1]); the
+`batch64` object is configs[3] (64 utterances per GPU) measured the same way (value, e2e, roofline, breakdown), and
+under torchrun every rank runs both, so the line carries the whole-job aggregate of each.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--frames F] [--cond-len Lc] [--no-batch64]
+  python bench.py --impl reference ...      # the UNMODIFIED reference (oracle/_ref, staged by build()) on the host cores;
+                                            # falls back to the oracle port when oracle/_ref is absent
 
 Prints ONE JSON line on rank 0.
 """
@@ -40,15 +45,19 @@ def parse():
     ap.add_argument("--cond-len", type=int, default=160)
     ap.add_argument("--ref-frames", type=int, default=128, help="frames per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch64", action="store_true", help="skip the 64-utterances-per-GPU leg")
+    ap.add_argument("--batch64-steps", type=int, default=2)
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the informative reference-torch-on-this-GPU timing")
     ap.add_argument("--layers", type=int, default=26, help="(debug) fewer layers; invalidates the number")
     return ap.parse_args()
 
 
-def config_dict(args, n_gpus):
+def config_dict(args, n_gpus, batch=None):
+    batch = args.batch if batch is None else batch
     return {"workload": "Zonos-v0.1-transformer random-init bf16, CFG 2.0, %d utterance(s)/GPU x %d frames (%.1f s) + DAC 44.1 kHz decode"
-                        % (args.batch, args.frames, args.frames / FRAME_RATE),
-            "baseline_config": "configs[1]" if args.batch == 1 else "configs[3]-shaped",
-            "batch_per_gpu": args.batch, "frames": args.frames, "cond_len": args.cond_len, "cfg_scale": 2.0,
+                        % (batch, args.frames, args.frames / FRAME_RATE),
+            "baseline_config": "configs[1]" if batch == 1 else ("configs[3]" if batch == 64 else "configs[3]-shaped"),
+            "batch_per_gpu": batch, "frames": args.frames, "cond_len": args.cond_len, "cfg_scale": 2.0,
             "sampling": "min_p=0.1, repetition_penalty=3.0 (generate defaults)", "n_layer": args.layers,
             "parallelism": "request-sharded replicas x%d, no data-path collective" % n_gpus,
             "l2": "each decode step streams 3.2 GB of weights (>> 126 MB L2), no flush needed"}
@@ -57,43 +66,52 @@ def config_dict(args, n_gpus):
 # --------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline and --impl reference): the reference's algorithm restated in oracle/
 # --------------------------------------------------------------------------------------------------
-def cpu_oracle_setup(args):
+def cpu_setup(args):
+    """The CPU arm: the unmodified reference from oracle/_ref when build() staged it (kind "reference"), else the oracle
+    port (kind "port").  Returns (kind, step_fn(frames) -> (audio_s, wall_s))."""
     import torch
-    from oracle.transformer import BackboneDims, TransformerOracle
     from zonos_b200.synthetic import TRANSFORMER_DIMS, make_backbone_weights, make_conditioning, make_dac_weights
+    from oracle import ref_runner
     dims = dict(TRANSFORMER_DIMS, n_layer=args.layers)
     torch.set_num_threads(os.cpu_count())
     w = make_backbone_weights(**dims, seed=0, heads_scale=8.0, eos_off=True)
-    oracle = TransformerOracle(w, BackboneDims(**dims), torch.bfloat16)
     cond = make_conditioning(2, args.cond_len, dims["d_model"])
-    return oracle, cond, make_dac_weights(seed=1), w
-
-
-def cpu_oracle_step(oracle, cond, dacw, frames):
-    """One bounded sample of the workload on the CPU: batch 1, `frames` new frames + their DAC decode."""
-    import torch
+    dacw = make_dac_weights(seed=1)
+    if ref_runner.available():
+        try:
+            model = ref_runner.build_model(dims, w, dacw)
+            del w
+            return "reference", lambda frames: ref_runner.step(model, cond, frames)
+        except Exception as e:                          # a dependency of the reference is missing on this box
+            print("reference unavailable, timing the oracle port instead: %r" % (e,), file=sys.stderr)
     from oracle import dac as o_dac, generate as o_gen
-    torch.manual_seed(420)
-    t0 = time.perf_counter()
-    codes = o_gen.generate(oracle, cond, None, frames, 2.0, 1, dict(min_p=0.1))
-    o_dac.decode(dacw, codes)
-    dt = time.perf_counter() - t0
-    return codes.shape[2] / FRAME_RATE, dt
+    from oracle.transformer import BackboneDims, TransformerOracle
+    oracle = TransformerOracle(w, BackboneDims(**dims), torch.bfloat16)
+
+    def port_step(frames):
+        torch.manual_seed(420)
+        t0 = time.perf_counter()
+        codes = o_gen.generate(oracle, cond, None, frames, 2.0, 1, dict(min_p=0.1))
+        o_dac.decode(dacw, codes)
+        return codes.shape[2] / FRAME_RATE, time.perf_counter() - t0
+    return "port", port_step
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is Python and
-    cannot travel to the GPU box) with all host threads, same config/metric, each step a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path (zonos/model.py:354-548 generate +
+    zonos/autoencoder.py:119-140 decode, unmodified, from oracle/_ref) with all host threads, same config/metric, each
+    step a bounded sample.  Rank 0 only: under torchrun the other ranks exit at once, so for N > 1 the driver's ratio
+    compares N GPUs with ONE host process (stated in `note`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    oracle, cond, dacw, _ = cpu_oracle_setup(args)
+    kind, step = cpu_setup(args)
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_oracle_step(oracle, cond, dacw, max(4, args.ref_frames // 4))
+        step(max(4, args.ref_frames // 4))
     audio = t = 0.0
     for _ in range(args.steps):
-        a, d = cpu_oracle_step(oracle, cond, dacw, args.ref_frames)
+        a, d = step(args.ref_frames)
         audio += a; t += d
     value = audio / t
     sample = "batch 1, Lc=%d prefill + %d frames + DAC decode per step (of the %d-frame utterance)" % (
@@ -101,8 +119,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(args, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "one host process on rank 0 (the reference's CPU path is single-process); with --gpus N > 1 a ratio against "
+                    "this line compares N GPUs with one host"}
     print(json.dumps(line), flush=True)
 
 
@@ -150,7 +170,6 @@ def measured_peaks():
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    import ctypes as C
     from zonos_b200 import DACAutoencoder, Zonos, ZonosConfig, _lib, transformer_config_dict
     from zonos_b200.synthetic import TRANSFORMER_DIMS, make_backbone_weights, make_conditioning, make_dac_weights
 
@@ -163,7 +182,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     dims = dict(TRANSFORMER_DIMS, n_layer=args.layers)
-    B, N, Lc = args.batch, args.frames, args.cond_len
+    N, Lc = args.frames, args.cond_len
 
     # every rank builds the same replica (seeded CPU generator) - no weight broadcast needed for synthetic runs
     w = make_backbone_weights(**dims, seed=0, heads_scale=8.0, eos_off=True)
@@ -171,112 +190,134 @@ def run_b200(args):
     model = Zonos(ZonosConfig.from_dict(transformer_config_dict(**dims)), autoencoder=DACAutoencoder(dacw, device=dev))
     model = model.to(dev, torch.bfloat16)
     model.load_state_dict(w)
-    cond_host = make_conditioning(2 * B, Lc, dims["d_model"], seed=1234 + rank).pin_memory()
-    cond_dev = cond_host.to(dev)
     ctx = model._ctx()
     stream = torch.cuda.current_stream(dev)
-
-    def step_device(seed):
-        codes = model.generate(cond_dev, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
-        wav = model.autoencoder.decode(codes)
-        return codes, wav
-
-    wav_host = torch.empty((B, 1, 512 * N), dtype=torch.float32).pin_memory()
-
-    def step_e2e(seed):
-        c = cond_host.to(dev, non_blocking=True)                       # H2D inside the timed region
-        codes = model.generate(c, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
-        wav = model.autoencoder.decode(codes)
-        wav_host[..., : wav.shape[-1]].copy_(wav, non_blocking=True)   # D2H of the result
-        torch.cuda.current_stream(dev).synchronize()
-        return codes, wav
+    peak, peak_src = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, K):
-        barrier()
-        l0 = ctx.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        frames = 0
-        for i in range(K):
-            codes, _ = fn(1000 + i)
-            frames += codes.shape[0] * codes.shape[2]
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1)
-        launches = ctx.launch_count() - l0
-        barrier()
-        t = torch.tensor([ms, float(frames)], dtype=torch.float64, device=dev)
-        if world > 1:
-            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            return float(tmax[0]), float(tsum[1]), launches
-        return ms, float(frames), launches
+    def measure(B, steps, warmup, with_clocks):
+        """One leg: `steps` passes (prefill + N frames + DAC decode) of B utterances per GPU.  value = inputs resident in
+        HBM; e2e = pinned host conditioning in, host waveform out, both copies inside the timed region."""
+        cond_host = make_conditioning(2 * B, Lc, dims["d_model"], seed=1234 + rank).pin_memory()
+        cond_dev = cond_host.to(dev)
+        wav_host = torch.empty((B, 1, 512 * N), dtype=torch.float32).pin_memory()
 
-    for i in range(max(args.warmup, 3)):
-        step_device(i)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    ms, frames, launches = timed(step_device, args.steps)
-    clock_info = clocks.stop() if rank == 0 else None
-    value = (frames / FRAME_RATE) / (ms / 1e3)
+        def step_device(seed):
+            codes = model.generate(cond_dev, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
+            wav = model.autoencoder.decode(codes)
+            return codes, wav
 
-    step_e2e(7)
-    ms_e, frames_e, _ = timed(step_e2e, args.steps)
-    e2e = (frames_e / FRAME_RATE) / (ms_e / 1e3)
+        def step_e2e(seed):
+            c = cond_host.to(dev, non_blocking=True)                       # H2D inside the timed region
+            codes = model.generate(c, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
+            wav = model.autoencoder.decode(codes)
+            wav_host[..., : wav.shape[-1]].copy_(wav, non_blocking=True)   # D2H of the result
+            torch.cuda.current_stream(dev).synchronize()
+            return codes, wav
 
-    # ---- roofline leg.  The dominant kernel is the persistent decode step (decode_step_kernel: one launch per codec
-    # frame = embed + 26 layers + heads, > 95 % of the pass).  Its average launch duration is measured live with CUDA
-    # events as the slope of generate() time over the number of steps (two lengths, same prefill), which also contains
-    # the 1-CTA sampler launch that follows every step.  Algorithmic bytes per launch per SURVEY.md 8(d):
-    # W (3.2 GB, out_proj counted once - its slice is held in shared memory for both passes) + KV read + KV append. ----
-    roof = None
-    breakdown = None
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-
-        def time_generate(n_frames, reps=2):
-            model.generate(cond_dev, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=5)
-            torch.cuda.synchronize(dev)
+        def timed(fn, K):
+            barrier()
+            l0 = ctx.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for r_ in range(reps):
-                c_ = model.generate(cond_dev, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=6 + r_)
+            frames = 0
+            for i in range(K):
+                codes, _ = fn(1000 + i)
+                frames += codes.shape[0] * codes.shape[2]
             e1.record(stream)
             torch.cuda.synchronize(dev)
-            return e0.elapsed_time(e1) / reps, c_
+            ms = e0.elapsed_time(e1)
+            launches = ctx.launch_count() - l0
+            barrier()
+            t = torch.tensor([ms, float(frames)], dtype=torch.float64, device=dev)
+            if world > 1:
+                tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+                return float(tmax[0]), float(tsum[1]), launches
+            return ms, float(frames), launches
 
-        n_small = max(8, N // 8)
-        t_full, codes_full = time_generate(N)
-        t_small, _ = time_generate(n_small)
-        step_ms = (t_full - t_small) / (N - n_small)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        model.autoencoder.decode(codes_full)
-        e0.record(stream)
-        for _ in range(3):
+        for i in range(warmup):
+            step_device(i)
+        clocks = ClockSampler(local)
+        if rank == 0 and with_clocks:
+            clocks.start()
+        ms, frames, launches = timed(step_device, steps)
+        clock_info = clocks.stop() if rank == 0 and with_clocks else None
+        value = (frames / FRAME_RATE) / (ms / 1e3)
+        step_e2e(7)
+        ms_e, frames_e, _ = timed(step_e2e, steps)
+        e2e = (frames_e / FRAME_RATE) / (ms_e / 1e3)
+
+        # ---- roofline leg.  The dominant kernel is the persistent decode step: one launch per codec frame = embed + all
+        # layers + heads, > 90 % of the pass (decode_step_kernel<R> for B <= 2, decode_tc_kernel above).  Its average
+        # launch duration is measured live with CUDA events as the slope of generate() time over the number of steps (two
+        # lengths, same prefill), which also contains the sampler launch that follows every step.  Algorithmic bytes per
+        # launch per SURVEY.md 8(d): W (3.2 GB, out_proj counted once) + KV read at the mean context + KV append. ----
+        roof = breakdown = None
+        if rank == 0:
+            def time_generate(n_frames, reps=2):
+                model.generate(cond_dev, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=5)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for r_ in range(reps):
+                    c_ = model.generate(cond_dev, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=6 + r_)
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                return e0.elapsed_time(e1) / reps, c_
+
+            n_small = max(8, N // 8)
+            reps = 2 if B <= 8 else 1
+            t_full, codes_full = time_generate(N, reps)
+            t_small, _ = time_generate(n_small, reps)
+            step_ms = (t_full - t_small) / (N - n_small)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             model.autoencoder.decode(codes_full)
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        dac_ms = e0.elapsed_time(e1) / 3
-        per_layer = (dims["n_heads"] + 2 * dims["n_heads_kv"]) * 128 * dims["d_model"] + dims["d_model"] ** 2 \
-            + 3 * dims["d_ff"] * dims["d_model"]
-        w_bytes = 2 * (dims["n_layer"] * per_layer + 9 * 1025 * dims["d_model"])
-        kv_tok = dims["n_layer"] * 2 * dims["n_heads_kv"] * 128 * 2
-        mean_s = Lc + 1 + (n_small + N + 16) / 2
-        step_bytes = w_bytes + 2 * B * mean_s * kv_tok + 2 * B * kv_tok + B * (9 * dims["d_model"] * 2 + 9 * 1025 * 4)
-        achieved = step_bytes / (step_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("decode_step_dram_bytes_per_launch")
+            e0.record(stream)
+            for _ in range(3):
+                model.autoencoder.decode(codes_full)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            dac_ms = e0.elapsed_time(e1) / 3
+            per_layer = (dims["n_heads"] + 2 * dims["n_heads_kv"]) * 128 * dims["d_model"] + dims["d_model"] ** 2 \
+                + 3 * dims["d_ff"] * dims["d_model"]
+            w_bytes = 2 * (dims["n_layer"] * per_layer + 9 * 1025 * dims["d_model"])
+            kv_tok = dims["n_layer"] * 2 * dims["n_heads_kv"] * 128 * 2
+            mean_s = Lc + 1 + (n_small + N + 16) / 2
+            step_bytes = w_bytes + 2 * B * mean_s * kv_tok + 2 * B * kv_tok + B * (9 * dims["d_model"] * 2 + 9 * 1025 * 4)
+            achieved = step_bytes / (step_ms * 1e-3) / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("batch%d_decode_step_dram_bytes_per_launch" % B)
+            if 2 * B <= 4:
+                kname = "decode_step_kernel<R=%d> (persistent FFMA2 consumer: embed + %d layers + heads, one launch per frame) + sample kernel" % (2 * B, dims["n_layer"])
+            else:
+                kname = "decode_tc_kernel, R=%d rows (persistent tcgen05/TMEM consumer + mma.sync attention: embed + %d layers + heads, one launch per frame) + sample kernel" % (2 * B, dims["n_layer"])
+            roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": peak_src, "us_per_launch": step_ms * 1e3, "algorithmic_bytes_per_launch": step_bytes,
+                    "how": "slope of generate() time between %d and %d frames (CUDA events)" % (n_small, N)}
+            steps_full = N + 8
+            breakdown = {"decode_ms": step_ms * steps_full, "prefill_and_setup_ms": max(0.0, t_full - step_ms * steps_full), "dac_ms": dac_ms}
+        return {"value": value, "ms_per_step": ms / steps, "frames_per_second": frames / (ms / 1e3), "launches": int(launches),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cond_host.numel() * 2, "d2h_bytes_per_step": wav_host.numel() * 4,
+                        "ms_per_step": ms_e / steps},
+                "clocks": clock_info, "roofline": roof, "breakdown_ms": breakdown, "cond_dev": cond_dev}
+
+    B = args.batch
+    head = measure(B, args.steps, max(args.warmup, 3), True)
+    cond_dev = head.pop("cond_dev")
+    roof = head["roofline"]
+
+    if rank == 0 and roof is not None and 2 * B <= 8:
+        # stand-alone norm2 + fc1 + SiLU GEMV (55 % of the weight bytes) in a C-side launch loop over all layers
         native = model._native_model()
         sp = _lib.stream_ptr(dev)
-        Rr = 2 * B if 2 * B <= 8 else 8
+        Rr = 2 * B
         iters = 8 * dims["n_layer"]
         ctx.check(ctx.lib.zb_bench_kernel(ctx.handle, native, 0, 2, Rr, dims["n_layer"], sp))
         torch.cuda.synchronize(dev)
@@ -287,16 +328,9 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         fc1_us = 1e3 * e0.elapsed_time(e1) / iters
         fc1_bytes = 2 * dims["d_ff"] * dims["d_model"] * 2 + Rr * dims["d_model"] * 2 + Rr * dims["d_ff"] * 2 + 4 * dims["d_model"]
-        roof = {"bound": "hbm", "kernel": "decode_step_kernel<R=%d> (persistent: embed + %d layers + heads, one launch per frame) + sample_kernel"
-                                          % (2 * B, dims["n_layer"]),
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "us_per_launch": step_ms * 1e3, "algorithmic_bytes_per_launch": step_bytes,
-                "how": "slope of generate() time between %d and %d frames (CUDA events)" % (n_small, N),
-                "gemv_fc1_alone": {"kernel": "gemv3_kernel (norm2+fc1+SiLU), PDL-chained launches over all layers",
-                                   "us_per_launch": fc1_us, "achieved_gbs": fc1_bytes / (fc1_us * 1e-6) / 1e9,
-                                   "frac": fc1_bytes / (fc1_us * 1e-6) / 1e9 / peak}}
-        steps_full = N + 8
-        breakdown = {"decode_ms": step_ms * steps_full, "prefill_and_setup_ms": max(0.0, t_full - step_ms * steps_full), "dac_ms": dac_ms}
+        roof["gemv_fc1_alone"] = {"kernel": "gemv3_kernel (norm2+fc1+SiLU), PDL-chained launches over all layers",
+                                  "us_per_launch": fc1_us, "achieved_gbs": fc1_bytes / (fc1_us * 1e-6) / 1e9,
+                                  "frac": fc1_bytes / (fc1_us * 1e-6) / 1e9 / peak}
 
     # ---- p50 time to first audio: generate_stream() entry -> first 43-frame (0.5 s) chunk decoded and on the host.  The
     # reference has no streaming (its TTFA is the whole generate + decode). ----
@@ -315,22 +349,55 @@ def run_b200(args):
         samples.sort()
         ttfa = {"p50_ms": samples[len(samples) // 2], "min_ms": samples[0], "max_ms": samples[-1], "chunk_frames": 43,
                 "definition": "generate_stream() entry -> first 0.5 s chunk DAC-decoded and copied to the host (prefill + 84 steps + chunk decode)"}
+    del cond_dev
+
+    # ---- the other half of the metric: 64 utterances per GPU (BASELINE.json configs[3]); every rank runs it ----
+    batch64 = None
+    if B == 1 and not args.no_batch64:
+        b64 = measure(64, max(1, args.batch64_steps), 1, False)
+        b64.pop("cond_dev")
+        if rank == 0:
+            batch64 = {"metric": METRIC, "value": b64["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": max(1, args.batch64_steps), "warmup": 1,
+                       "ms_per_step": b64["ms_per_step"], "frames_per_second": b64["frames_per_second"], "e2e": b64["e2e"],
+                       "gpu_launches": b64["launches"], "roofline": b64["roofline"], "breakdown_ms": b64["breakdown_ms"],
+                       "config": config_dict(args, n_gpus, 64), "target_audio_s_per_s_per_box_of_8": 3000.0}
+
+    # ---- informative: the reference's own torch path on THIS GPU (eager; SURVEY K1/K2/K16 bars), bounded sample ----
+    ref_gpu = None
+    if rank == 0 and not args.no_ref_gpu and B == 1:
+        try:
+            from oracle import ref_runner
+            if ref_runner.available():
+                rm = ref_runner.build_model(dims, w, dacw, device=dev)
+                rc = make_conditioning(2, Lc, dims["d_model"], seed=1234).to(dev)
+                ref_runner.step(rm, rc, 16)
+                n_a, n_b = max(16, args.ref_frames // 4), args.ref_frames
+                a0_, d0_ = ref_runner.step(rm, rc, n_a)
+                a_, d_ = ref_runner.step(rm, rc, n_b)
+                ref_gpu = {"value": a_ / d_, "unit": UNIT, "sample": "batch 1, Lc=%d prefill + %d frames + DAC decode, wall clock" % (Lc, n_b),
+                           "ms_per_decode_step": 1e3 * (d_ - d0_) / (n_b - n_a),
+                           "how": "value: one whole call (its per-call setup, e.g. CUDA-graph capture, included); ms_per_decode_step: slope "
+                                  "between %d and %d frames" % (n_a, n_b),
+                           "what": "unmodified reference (zonos torch backbone + transformers DAC) on this GPU, its own code path"}
+                del rm
+                torch.cuda.empty_cache()
+        except Exception as e:
+            ref_gpu = {"unavailable": repr(e)[:300]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         del w
-        oracle, cond, dacw_c, _ = cpu_oracle_setup(args)
-        a, d = cpu_oracle_step(oracle, cond, dacw_c, args.ref_frames)
-        cpu = {"value": a / d, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        kind, cstep = cpu_setup(args)
+        a, d = cstep(args.ref_frames)
+        cpu = {"value": a / d, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                "sample": "batch 1, Lc=%d prefill + %d frames + DAC decode (%.1f s of CPU work)" % (Lc, args.ref_frames, d)}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic", "config": config_dict(args, n_gpus), "frames_per_second": frames / (ms / 1e3),
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cond_host.numel() * 2, "d2h_bytes_per_step": wav_host.numel() * 4,
-                        "ms_per_step": ms_e / args.steps},
-                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof, "breakdown_ms": breakdown, "ttfa": ttfa, "cpu_baseline": cpu}
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": config_dict(args, n_gpus), "frames_per_second": head["frames_per_second"],
+                "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"], "roofline": roof,
+                "breakdown_ms": head["breakdown_ms"], "ttfa": ttfa, "batch64": batch64, "reference_gpu_eager": ref_gpu, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -48,6 +48,27 @@ def test_no_cpu_fallback():
         _lib.Context(0)          # no device: zb_ctx_create fails loudly
 
 
+def test_torch_custom_ops_are_registered_and_have_no_cpu_path():
+    """north_star: "thin PyTorch custom ops over a C-ABI layer" - zonos_b200/ops.py registers torch.ops.zonos_b200.*; every
+    op refuses CPU tensors (no fallback) and has a fake implementation (shape inference without a GPU)."""
+    from zonos_b200 import ops
+    for name in ops.OPS:
+        assert hasattr(torch.ops.zonos_b200, name), name
+    codes = torch.zeros(2, 9, 5, dtype=torch.int64)
+    with pytest.raises(RuntimeError):
+        torch.ops.zonos_b200.embed_codes(0, codes, 2, 256)
+    with pytest.raises(RuntimeError):
+        torch.ops.zonos_b200.dac_decode(0, codes, 512)
+    with pytest.raises(RuntimeError):
+        torch.ops.zonos_b200.sample_update(torch.zeros(1, 9, 1025), None, None, [1.0, 0.0, 0.1, 0.0, 0.0, 0.0, 3.0], 0, 2, 0, 0, False)
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        c = torch.zeros(2, 9, 5, dtype=torch.int64)
+        assert torch.ops.zonos_b200.embed_codes(0, c, 2, 256).shape == (4, 5, 256)
+        assert torch.ops.zonos_b200.dac_decode(0, c, 512).shape == (2, 1, 2560)
+        assert torch.ops.zonos_b200.heads_cfg(0, torch.zeros(4, 256, dtype=torch.bfloat16), 2.0, 9, 1025).shape == (2, 9, 1025)
+
+
 def test_host_codebook_pattern_matches_oracle():
     from zonos_b200 import apply_delay_pattern, revert_delay_pattern
     g = torch.Generator().manual_seed(3)

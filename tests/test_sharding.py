@@ -5,7 +5,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from zonos_b200.sharding import batch_global_truncate, generate_sharded, shard_conditioning, shard_range
+from zonos_b200.sharding import batch_global_align, generate_sharded, shard_conditioning, shard_range
 
 
 def test_shard_range_is_a_partition():
@@ -33,7 +33,7 @@ def test_shard_conditioning_keeps_cfg_pairs_together():
 def _fake_generate(cond, audio_prefix_codes=None, batch_size=1, max_new_tokens=8, **kw):
     # deterministic stand-in: codes depend only on the utterance's own cond row; length depends on the shard
     ids = cond[:batch_size, 0, 0].long()
-    n = max_new_tokens - int(ids.min()) % 3
+    n = max_new_tokens - 3 * (int(ids.min()) % 2)
     return (ids.view(-1, 1, 1) * 10 + torch.arange(n).view(1, 1, n)).expand(batch_size, 9, n).contiguous()
 
 
@@ -56,8 +56,25 @@ def test_generate_sharded_world2_gloo(tmp_path):
     res = torch.load(out)
     B = 5
     cond = torch.arange(2 * B).float().view(2 * B, 1, 1).expand(2 * B, 2, 4)
-    # every utterance keeps its own tokens (no cross-rank mixing) and the batch is cut at one common length
+    # every utterance keeps its own tokens (no cross-rank mixing); the batch has the length of the LONGEST per-rank result
     parts = [_fake_generate(shard_conditioning(cond, B, 2, r), batch_size=shard_range(B, 2, r)[1] - shard_range(B, 2, r)[0]) for r in range(2)]
-    want = batch_global_truncate(parts)
-    assert res.shape == want.shape and torch.equal(res, want)
+    assert parts[0].shape[-1] != parts[1].shape[-1]          # the ranks really finish at different lengths
+    n_long = max(p.shape[-1] for p in parts)
+    assert res.shape == (B, 9, n_long)
+    row = 0
+    for p in parts:
+        for u in range(p.shape[0]):
+            assert torch.equal(res[row, :, :p.shape[-1]], p[u])                   # nothing cut, nothing mixed
+            assert (res[row, :, p.shape[-1]:] == 512).all()                       # what the reference emits after an utterance's end
+            row += 1
     assert res[:, 0, 0].tolist() == [0, 10, 20, 30, 40]
+
+
+def test_batch_global_align_keeps_the_longest_utterance():
+    """A rank with a short utterance must not truncate another rank's long one (zonos/utilities/tensor_ops.py:95: a batch
+    runs until ALL rows are done)."""
+    short = torch.arange(2 * 9 * 20).view(2, 9, 20) % 1000
+    long_ = torch.arange(1 * 9 * 100).view(1, 9, 100) % 1000
+    out = batch_global_align([short, long_])
+    assert out.shape == (3, 9, 100)
+    assert torch.equal(out[2], long_[0]) and torch.equal(out[:2, :, :20], short) and (out[:2, :, 20:] == 512).all()

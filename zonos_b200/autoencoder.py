@@ -87,15 +87,7 @@ class DACAutoencoder:
         """zonos/autoencoder.py:119-140: int64 [B,Q,T] -> fp32 [B,1,512*T]."""
         assert codes.dim() == 3 and codes.shape[1] == self.num_codebooks
         codes = codes.to(self.device, torch.int64).contiguous()
-        B, _, T = codes.shape
-        up = math.prod(DAC_STRIDES)
-        wav = torch.empty((B, 1, up * T), dtype=torch.float32, device=self.device)
-        if T == 0:
-            return wav
-        ctx = _lib.context(self.device)
-        with ctx.lock:
-            ctx.check(ctx.lib.zb_dac_decode(ctx.handle, self._handle, _lib.ptr(codes), B, T, _lib.ptr(wav), _lib.stream_ptr(self.device)))
-        return wav
+        return torch.ops.zonos_b200.dac_decode(self._handle.value, codes, math.prod(DAC_STRIDES))
 
     def decode_to_int16(self, codes: torch.Tensor):
         """zonos/autoencoder.py:142-170."""

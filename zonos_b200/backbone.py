@@ -128,31 +128,43 @@ class B200ZonosBackbone(nn.Module):
         # (zonos/backbone/_mamba_ssm.py): out_proj once, rotate-half RoPE with cos/sin cached in bf16, norm per `rms_norm`.
         self.out_proj_repeats = 1 if self.hybrid else 2
         self.rope_interleaved = not self.hybrid
-        self._native = None       # (key, handle, keepalive)
+        self._handles = {}        # key -> (zb_model handle, keepalive)
+        self._tables = None       # (embeddings, heads, n_codebooks, head_vocab) registered by the owning Zonos
+        self._rope = None
         self._cache: PagedKVCache | None = None
 
     # ---- native model handle ------------------------------------------------------------------
     def _weights_key(self):
         return tuple(p.data_ptr() for p in self.parameters()) + (self.out_proj_repeats, self.rope_interleaved)
 
+    def register_tables(self, embeddings, heads, n_codebooks=9, head_vocab=1025):
+        """The owner of the embedding tables / fused heads (`Zonos`) registers them once, so that the plugin-level
+        `forward()` and the model-level calls share ONE native handle instead of re-creating it back and forth."""
+        self._tables = (list(embeddings), heads, n_codebooks, head_vocab)
+
     def native_model(self, embeddings=None, heads=None, n_codebooks=9, head_vocab=1025):
-        """zb_model for the current weights (+ optional embedding tables / fused heads owned by the caller)."""
+        """zb_model for the current weights (+ the registered or given embedding tables / fused heads).  Handles are
+        cached per (weights, tables) key and only released with the module: a live generate session keeps a pointer to
+        its zb_model, so a handle must never be destroyed because another call shape came along."""
         p0 = next(self.parameters())
         if p0.device.type != "cuda" or p0.dtype != torch.bfloat16:
             raise RuntimeError("B200ZonosBackbone needs bf16 weights on a CUDA device (model.to(device, torch.bfloat16))")
+        if embeddings is None and heads is None and self._tables is not None:
+            embeddings, heads, n_codebooks, head_vocab = self._tables
         key = self._weights_key() + tuple(e.data_ptr() for e in (embeddings or [])) + ((heads.data_ptr(),) if heads is not None else ())
-        if self._native is not None and self._native[0] == key:
-            return self._native[1]
-        if self._native is not None:
-            _lib.load().zb_model_destroy(self._native[1])
-            self._native = None
+        hit = self._handles.get(key)
+        if hit is not None:
+            return hit[0]
         cfg = self.config
         ctx = _lib.context(p0.device)
         H, Hkv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
         hd = cfg.d_model // H
-        rope = rotary_table(ROPE_TABLE_LEN, hd, device=p0.device)
-        if self.hybrid:      # flash_attn RotaryEmbedding keeps cos/sin in the activation dtype
-            rope = rope.to(torch.bfloat16).float().contiguous()
+        if self._rope is None or self._rope.device != p0.device:
+            rope = rotary_table(ROPE_TABLE_LEN, hd, device=p0.device)
+            if self.hybrid:      # flash_attn RotaryEmbedding keeps cos/sin in the activation dtype
+                rope = rope.to(torch.bfloat16).float().contiguous()
+            self._rope = rope
+        rope = self._rope
         layers = (_lib.zb_layer * cfg.n_layer)()
         mm = None
         for i, blk in enumerate(self.layers):
@@ -188,8 +200,16 @@ class B200ZonosBackbone(nn.Module):
         h = C.c_void_p()
         with ctx.lock:
             ctx.check(ctx.lib.zb_model_create(ctx.handle, C.byref(d), C.byref(h)))
-        self._native = (key, h, (rope, layers, emb_arr))
+        self._handles[key] = (h, (rope, layers, emb_arr))
         return h
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for h, _ in getattr(self, "_handles", {}).values():
+                lib.zb_model_destroy(h)
+        except Exception:
+            pass
 
     # ---- reference plugin contract ---------------------------------------------------------------
     def allocate_inference_cache(self, batch_size: int, max_seqlen: int, dtype: torch.dtype = torch.bfloat16):
@@ -220,14 +240,10 @@ class B200ZonosBackbone(nn.Module):
         lengths = inference_params.lengths_per_sample
         if not lengths.is_cuda:
             raise RuntimeError("lengths_per_sample must live on the model's device")
-        model = self.native_model()
-        ctx = _lib.context(x.device)
-        y = torch.empty((R, 1 if last_only else T, D), dtype=x.dtype, device=x.device)
-        cache = self._cache.desc(lengths)
-        with ctx.lock:
-            ctx.check(ctx.lib.zb_backbone_forward(ctx.handle, model, C.byref(cache), _lib.ptr(x), T, int(last_only),
-                                                  _lib.ptr(y), _lib.stream_ptr(x.device)))
-        return y
+        assert lengths.dtype == torch.int32 and lengths.numel() >= R
+        c = self._cache
+        return torch.ops.zonos_b200.backbone_forward(self.native_model().value, x, c.kv_pages, c.page_table, lengths, c.conv_state,
+                                                     c.ssm_state, bool(last_only))
 
 
 # Same registry shape as zonos/backbone/__init__.py:24-36.  This framework has one implementation, so every

@@ -80,7 +80,7 @@ zb_status zb_ctx_create(int32_t device, zb_ctx** out) {
 
 zb_status zb_ctx_destroy(zb_ctx* ctx) {
   if (!ctx) return ZB_OK;
-  cudaSetDevice(ctx->device);
+  zb_device_guard dev_guard(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->dac_scratch) cudaFree(ctx->dac_scratch);
   if (ctx->tc_ws) cudaFree(ctx->tc_ws);
@@ -100,6 +100,7 @@ int64_t zb_launch_count(const zb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 // ---------------------------------------------------------------------------------------------
 zb_status zb_model_create(zb_ctx* ctx, const zb_model_desc* desc, zb_model** out) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, desc && out, "zb_model_create: null argument");
   ZB_REQUIRE(ctx, desc->n_layer >= 1 && desc->layers, "zb_model_create: no layers");
   ZB_REQUIRE(ctx, desc->d_model % 256 == 0, "zb_model_create: d_model %d must be a multiple of 256", desc->d_model);
@@ -132,6 +133,7 @@ zb_status zb_model_destroy(zb_model* model) { delete model; return ZB_OK; }
 zb_status zb_embed_codes(zb_ctx* ctx, const zb_model* model, const int64_t* codes, int64_t stride_b, int64_t stride_q,
                          int64_t stride_t, int32_t B, int32_t T, int32_t repeat, void* out, zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, model && codes && out && B >= 1 && T >= 1 && repeat >= 1, "zb_embed_codes: bad arguments");
   ZB_REQUIRE(ctx, (int)model->emb.size() == model->d.n_codebooks, "zb_embed_codes: model has no embedding tables");
   zb_embed_launch L;
@@ -143,6 +145,7 @@ zb_status zb_embed_codes(zb_ctx* ctx, const zb_model* model, const int64_t* code
 zb_status zb_backbone_forward(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const void* x, int32_t T, int32_t last_only,
                               void* y, zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, model && cache && x && y && T >= 1, "zb_backbone_forward: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const zb_model_desc& d = model->d;
@@ -162,6 +165,7 @@ zb_status zb_backbone_forward(zb_ctx* ctx, const zb_model* model, const zb_cache
 zb_status zb_heads_cfg(zb_ctx* ctx, const zb_model* model, const void* hidden, int64_t row_stride, int32_t R, float cfg_scale,
                        float* logits, zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, model && hidden && logits && R >= 1 && model->d.heads, "zb_heads_cfg: bad arguments");
   return zb_launch_heads(ctx, model, (const bf16*)hidden, row_stride, R, 0, cfg_scale, logits, nullptr, 0, (cudaStream_t)stream);
 }
@@ -170,6 +174,7 @@ zb_status zb_sample_from_logits(zb_ctx* ctx, const zb_sampling* params, const fl
                                 const int64_t* window, int64_t win_stride_b, int64_t win_stride_q, int32_t W, const float* q,
                                 uint64_t seed, uint64_t draw_index, int32_t apply_logit_bias, int64_t* tokens, zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, params && logits && tokens, "zb_sample_from_logits: null argument");
   zb_sample_launch L;
   L.logits = logits; L.B = B; L.Q = Q; L.V = V; L.window = window; L.wsb = win_stride_b; L.wsq = win_stride_q; L.W = W;
@@ -246,6 +251,7 @@ extern "C" {
 zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const zb_gen_desc* desc, zb_gen** out,
                             zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, model && cache && desc && out, "zb_generate_begin: null argument");
   const zb_model_desc& md = model->d;
   const int B = desc->B, R = 2 * B, Q = desc->Q;
@@ -367,6 +373,7 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
 zb_status zb_generate_steps(zb_gen* gen, int32_t n_steps, zb_stream stream) {
   if (!gen) return ZB_ERR_INVALID;
   zb_ctx* ctx = gen->ctx;
+  zb_device_guard dev_guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   for (int i = 0; i < n_steps && gen->steps_enqueued < gen->max_steps; ++i) {
     if (gen->mega) {
@@ -383,6 +390,7 @@ zb_status zb_generate_steps(zb_gen* gen, int32_t n_steps, zb_stream stream) {
 zb_status zb_generate_poll(zb_gen* gen, zb_gen_progress* out, zb_stream stream) {
   if (!gen || !out) return ZB_ERR_INVALID;
   zb_ctx* ctx = gen->ctx;
+  zb_device_guard dev_guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   int32_t* tmp = gen->st_host + 8;                 // second half of the pinned block: staging for an exact read-back
   ZB_CUDA(ctx, cudaMemcpyAsync(tmp, gen->st, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -406,6 +414,7 @@ zb_status zb_generate_peek(zb_gen* gen, zb_gen_progress* out) {
 
 zb_status zb_generate_end(zb_gen* gen) {
   if (!gen) return ZB_OK;
+  zb_device_guard dev_guard(gen->ctx);
   if (gen->pinned) gen->ctx->scratch_pins--;
   if (gen->graph) cudaGraphExecDestroy(gen->graph);
   if (gen->slab >= 0) gen->ctx->gen_slabs[gen->slab].in_use = false;   // the memory stays with the context for the next session

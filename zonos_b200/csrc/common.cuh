@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/zonos_b200.h"
@@ -42,7 +43,32 @@ struct zb_ctx {
   int32_t* counters = nullptr;  // zeroed int32 words for last-CTA-done patterns
   cudaStream_t capture_stream = nullptr;   // graph capture happens here (the caller's stream may be the legacy one)
   std::vector<zb_gen_slab> gen_slabs;      // session memory, reused across generate calls
-  size_t max_dyn_smem_tc = 0;              // cudaFuncAttributeMaxDynamicSharedMemorySize set on this device for decode_tc_kernel
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE setting: high-water mark per kernel for this context's device
+  std::unordered_map<const void*, size_t> smem_attr;
+};
+
+// Raise the dynamic shared-memory limit of `kernel` on the context's device if it is below `smem`.
+template <typename K>
+inline cudaError_t zb_ensure_smem(zb_ctx* ctx, K kernel, size_t smem) {
+  size_t& cur = ctx->smem_attr[reinterpret_cast<const void*>(kernel)];
+  if (cur >= smem) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) cur = smem;
+  return e;
+}
+
+// Every extern "C" entry point runs on the context's device, whatever device the calling thread has current
+// (the reference wraps generate in `with torch.device(device)`), and restores the caller's device on return.
+struct zb_device_guard {
+  int prev = -1;
+  explicit zb_device_guard(const zb_ctx* ctx) {
+    if (!ctx) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device && cudaSetDevice(ctx->device) == cudaSuccess) prev = cur;
+  }
+  ~zb_device_guard() { if (prev >= 0) cudaSetDevice(prev); }
+  zb_device_guard(const zb_device_guard&) = delete;
+  zb_device_guard& operator=(const zb_device_guard&) = delete;
 };
 
 extern thread_local std::string g_zb_create_error;

@@ -413,11 +413,7 @@ zb_status run_conv(zb_ctx* ctx, const zb_conv_w& c, const bf16* in, int B, int L
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * (a_bytes + b_bytes) + 1024;
-  static size_t attr = 0;
-  if (smem > attr) {
-    ZB_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  ZB_CUDA(ctx, zb_ensure_smem(ctx, conv_tc_kernel, smem));
   dim3 grid((a.rows + 127) / 128, ntiles, B);
   conv_tc_kernel<<<grid, CV_THREADS, smem, s>>>(p);
   ZB_CHECK_LAUNCH(ctx);
@@ -427,6 +423,7 @@ zb_status run_conv(zb_ctx* ctx, const zb_conv_w& c, const bf16* in, int B, int L
 
 extern "C" zb_status zb_dac_create(zb_ctx* ctx, const zb_dac_desc* desc, zb_dac** out, zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, desc && out, "zb_dac_create: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int Q = desc->n_codebooks, nb = desc->n_blocks;
@@ -476,6 +473,7 @@ extern "C" zb_status zb_dac_create(zb_ctx* ctx, const zb_dac_desc* desc, zb_dac*
 
 extern "C" zb_status zb_dac_destroy(zb_dac* dac) {
   if (!dac) return ZB_OK;
+  zb_device_guard dev_guard(dac->ctx);
   for (void* p : dac->owned) cudaFree(p);
   delete dac;
   return ZB_OK;
@@ -484,6 +482,7 @@ extern "C" zb_status zb_dac_destroy(zb_dac* dac) {
 extern "C" zb_status zb_dac_decode(zb_ctx* ctx, const zb_dac* dac, const int64_t* codes, int32_t B, int32_t T, float* wav,
                                    zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, dac && codes && wav && B >= 1 && T >= 1, "zb_dac_decode: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const zb_dac_desc& d = dac->d;

@@ -1563,11 +1563,7 @@ Scratch carve(const zb_model* mdl, void* base, int M, int nsplit, size_t* total)
 template <int MT, int PRO, int EPI>
 zb_status launch_gemv_t(zb_ctx* ctx, GemvArgs& a, int mtiles, cudaStream_t stream) {
   const size_t smem = (size_t)MT * a.K * 2;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    ZB_CUDA(ctx, cudaFuncSetAttribute(gemv_kernel<MT, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  if (smem > 48 * 1024) ZB_CUDA(ctx, zb_ensure_smem(ctx, gemv_kernel<MT, PRO, EPI>, smem));
   const int npairs = (EPI == EPI_SILU) ? a.F : (a.N + 1) / 2;
   int gx = (npairs + kWarps - 1) / kWarps;
   const int cap = ctx->num_sms * 2;                 // two CTAs of 8 warps per SM keep >32 KB of loads in flight
@@ -1600,11 +1596,7 @@ zb_status launch_gemv3_t(zb_ctx* ctx, GemvArgs& a, cudaStream_t stream) {
   const int nrows_pad = (nrows_max + RPS - 1) / RPS * RPS;
   const size_t smem = (size_t)stages * stage_bytes + (size_t)nrows_pad * KS * R * sizeof(float);
   ZB_REQUIRE(ctx, smem <= 220 * 1024, "gemv3: %zu bytes of shared memory", smem);
-  static size_t attr = 0;
-  if (smem > attr) {
-    ZB_CUDA(ctx, cudaFuncSetAttribute(gemv3_kernel<R, NC, RW, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  ZB_CUDA(ctx, zb_ensure_smem(ctx, gemv3_kernel<R, NC, RW, PRO, EPI>, smem));
   ZB_CUDA(ctx, zb_launch_pdl(gemv3_kernel<R, NC, RW, PRO, EPI>, dim3(grid), dim3((kW3 + 1) * 32), smem, stream, a));
   ctx->launches++;
   return ZB_OK;
@@ -1982,12 +1974,7 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
   m.evict_first = evict_first;
   const size_t smem = (size_t)stages * kMegaStageBytes + pb + attn_bytes;
   auto launch = [&](auto kernel) -> zb_status {
-    static size_t attr[2] = {0, 0};                      // per kernel instantiation (R <= 2, R <= 4): the generic lambda is ONE function for both
-    size_t& cur = attr[R <= 2 ? 0 : 1];
-    if (smem > cur) {
-      ZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cur = smem;
-    }
+    ZB_CUDA(ctx, zb_ensure_smem(ctx, kernel, smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3((kMW + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute at[1];
@@ -2010,6 +1997,7 @@ unsigned long long* zb_debug_steplog_ptr() { return g_steplog; }
 extern "C" zb_status zb_bench_kernel(zb_ctx* ctx, const zb_model* model, int32_t layer, int32_t which, int32_t rows, int32_t iters,
                                      zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   ZB_REQUIRE(ctx, model && layer >= 0 && layer < model->d.n_layer && rows >= 1 && rows <= 8 && iters >= 1, "zb_bench_kernel: bad arguments");
   const zb_model_desc& d = model->d;
   const size_t need = zb_backbone_scratch_bytes(model, rows, 1, ZB_PAGE_TOKENS) + (size_t)rows * d.d_model * 2 + 256;

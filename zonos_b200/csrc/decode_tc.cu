@@ -1105,10 +1105,7 @@ zb_status zb_launch_decode_tc(zb_ctx* ctx, const zb_model* model, const zb_cache
   a.bar = bar; a.loop = loop; a.nbar = 2 + d.n_layer * (7 + 2 * d.out_proj_repeats);
   a.stages = p.stages; a.bstages = p.bstages; a.bslot_bytes = p.bslot_bytes; a.na = p.na;
   a.scale = 1.0f / sqrtf((float)d.head_dim); a.timeline = g_tc_timeline;
-  if (ctx->max_dyn_smem_tc < p.smem) {                 // per context (= per device), not per process
-    ZB_CUDA(ctx, cudaFuncSetAttribute(decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    ctx->max_dyn_smem_tc = p.smem;
-  }
+  ZB_CUDA(ctx, zb_ensure_smem(ctx, decode_tc_kernel, p.smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctx->num_sms); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = stream;
   cudaLaunchAttribute at[1];

@@ -314,11 +314,7 @@ zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t strea
   a.stages = stages;
   size_t smem = (size_t)stages * (a_bytes + b_bytes) + 1024;
   if ((size_t)128 * BN * 4 + 1024 > smem) smem = (size_t)128 * BN * 4 + 1024;     // epilogue exchange buffer reuses the ring
-  static size_t attr = 0;
-  if (smem > attr) {
-    ZB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  ZB_CUDA(ctx, zb_ensure_smem(ctx, gemm_tc_kernel, smem));
   const int ntiles = (g.epi == TEPI_SILU) ? (g.F + 63) / 64 : (g.N + TC_BM - 1) / TC_BM;
   // split-K for the bandwidth-bound small-M regime: enough CTAs to pull weights with every SM
   int ksplit = 1;
@@ -350,6 +346,7 @@ zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t strea
 // diagnostics: plain Y = X W^T (bf16) for tests
 extern "C" ZB_API zb_status zb_debug_gemm(zb_ctx* ctx, const void* x, const void* w, void* y, int32_t M, int32_t N, int32_t K, zb_stream stream) {
   if (!ctx) return ZB_ERR_INVALID;
+  zb_device_guard dev_guard(ctx);
   zb_gemm_tc g;
   g.W = (const bf16*)w; g.x = (const bf16*)x; g.ldx = K; g.M = M; g.N = N; g.K = K; g.epi = TEPI_STORE; g.y = (bf16*)y; g.ldy = N;
   return zb_launch_gemm_tc(ctx, g, (cudaStream_t)stream);

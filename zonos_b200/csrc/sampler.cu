@@ -716,13 +716,9 @@ zb_status zb_launch_sample(zb_ctx* ctx, const zb_sample_launch& L, cudaStream_t 
   size_t smem = 0;
   if (L.sp.temperature > 0.f && (L.sp.top_p > 0.f || L.sp.top_k > 0)) smem = (size_t)L.Q * SAMP_SORTN * 8;
   ZB_REQUIRE(ctx, smem <= 227 * 1024, "sampler: top-p/top-k with Q=%d codebooks needs %zu bytes of shared memory", L.Q, smem);
-  static size_t attr[2] = {0, 0};
   const int variant = L.Q <= 9 ? 0 : 1;
   auto kernel = variant == 0 ? sample_kernel<288> : sample_kernel<512>;
-  if (smem > 48 * 1024 && smem > attr[variant]) {
-    ZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[variant] = smem;
-  }
+  if (smem > 48 * 1024) ZB_CUDA(ctx, zb_ensure_smem(ctx, kernel, smem));
   static const int wide = getenv("ZB_SAMPLER_WIDE") ? atoi(getenv("ZB_SAMPLER_WIDE")) : 1;
   if (wide && smem == 0 && L.V <= SAMPW_NPER * SAMPW_THREADS && L.B <= ZB_MAX_B) {     // no sort needed: one CTA of 4 warps per codebook row
     ZB_CUDA(ctx, zb_launch_pdl(sample_wide_kernel, dim3(L.B, L.Q), dim3(SAMPW_THREADS), 0, stream, a));

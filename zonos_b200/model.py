@@ -13,7 +13,7 @@ from typing import Callable
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, ops  # noqa: F401  (ops registers torch.ops.zonos_b200.*)
 from .autoencoder import DACAutoencoder
 from .backbone import BACKBONES, B200ZonosBackbone
 from .codebook_pattern import apply_delay_pattern, revert_delay_pattern
@@ -109,7 +109,8 @@ class Zonos(nn.Module):
 
     # ---------------------------------------------------------------- native handles -----------
     def _native_model(self):
-        return self.backbone.native_model([e.weight for e in self.embeddings], self.fused_heads.weight, self.num_codebooks, 1025)
+        self.backbone.register_tables([e.weight for e in self.embeddings], self.fused_heads.weight, self.num_codebooks, 1025)
+        return self.backbone.native_model()
 
     def _ctx(self):
         return _lib.context(self.device)
@@ -119,37 +120,20 @@ class Zonos(nn.Module):
         """zonos/model.py:179-192: int64 [B,Q,T] -> bf16 [B*repeat,T,D] (sum of the Q codebook embeddings)."""
         B, Q, T = codes.shape
         assert Q == self.num_codebooks
-        codes = codes.to(torch.int64)
-        out = torch.empty((B * repeat, T, self.config.backbone.d_model), dtype=torch.bfloat16, device=self.device)
-        ctx = self._ctx()
-        with ctx.lock:
-            ctx.check(ctx.lib.zb_embed_codes(ctx.handle, self._native_model(), _lib.ptr(codes), codes.stride(0), codes.stride(1),
-                                             codes.stride(2), B, T, repeat, _lib.ptr(out), _lib.stream_ptr(self.device)))
-        return out
+        codes = codes.to(self.device, torch.int64)
+        return torch.ops.zonos_b200.embed_codes(self._native_model().value, codes, repeat, self.config.backbone.d_model)
 
     def apply_heads(self, hidden_states: torch.Tensor) -> torch.Tensor:
         """zonos/model.py:194-206: bf16 [R,T,D] -> [R,Q,T,1025] (returned in fp32; the reference casts right after)."""
         R, T, D = hidden_states.shape
         h = hidden_states.contiguous().view(R * T, D)
-        logits = torch.empty((R * T, self.num_codebooks, 1025), dtype=torch.float32, device=h.device)
-        ctx = self._ctx()
-        with ctx.lock:
-            ctx.check(ctx.lib.zb_heads_cfg(ctx.handle, self._native_model(), _lib.ptr(h), D, R * T, 1.0, _lib.ptr(logits),
-                                           _lib.stream_ptr(h.device)))
+        logits = torch.ops.zonos_b200.heads_cfg(self._native_model().value, h, 1.0, self.num_codebooks, 1025)
         return logits.view(R, T, self.num_codebooks, 1025).transpose(1, 2)
 
     def _compute_logits(self, hidden_states: torch.Tensor, inference_params: InferenceParams, cfg_scale: float) -> torch.Tensor:
         """zonos/model.py:225-234: backbone -> last token -> heads -> fp32 -> CFG mix; [R,T,D] -> [B,Q,1025]."""
         last = self.backbone(hidden_states, inference_params, last_only=True)[:, 0]
-        R, D = last.shape
-        cfg_scale = float(cfg_scale)
-        rows = R // 2 if cfg_scale != 1.0 else R
-        logits = torch.empty((rows, self.num_codebooks, 1025), dtype=torch.float32, device=last.device)
-        ctx = self._ctx()
-        with ctx.lock:
-            ctx.check(ctx.lib.zb_heads_cfg(ctx.handle, self._native_model(), _lib.ptr(last), D, R, cfg_scale, _lib.ptr(logits),
-                                           _lib.stream_ptr(last.device)))
-        return logits
+        return torch.ops.zonos_b200.heads_cfg(self._native_model().value, last, float(cfg_scale), self.num_codebooks, 1025)
 
     def setup_cache(self, batch_size: int, max_seqlen: int, dtype: torch.dtype = torch.bfloat16) -> InferenceParams:
         """zonos/model.py:305-338."""
@@ -244,7 +228,7 @@ class Zonos(nn.Module):
                     cur = torch.cuda.current_stream(device)
                     while enq < max_steps:
                         n = min(POLL_EVERY, max_steps - enq)
-                        ctx.check(lib.zb_generate_steps(gen, n, stream))
+                        torch.ops.zonos_b200.decode_step(gen.value, n, delayed, params.lengths_per_sample)
                         enq += n
                         ev = torch.cuda.Event()
                         ev.record(cur)
@@ -256,7 +240,7 @@ class Zonos(nn.Module):
                                 break
                 else:
                     for step in range(max_steps):                           # reference cadence: one host visit per step
-                        ctx.check(lib.zb_generate_steps(gen, 1, stream))
+                        torch.ops.zonos_b200.decode_step(gen.value, 1, delayed, params.lengths_per_sample)
                         ctx.check(lib.zb_generate_poll(gen, C.byref(prog), stream))
                         if prog.done:
                             break
@@ -328,34 +312,47 @@ class Zonos(nn.Module):
             wav = self.autoencoder.decode(part)
             return wav[..., 512 * (lo - ctx_lo):512 * (hi - ctx_lo)], part[..., lo - ctx_lo:hi - ctx_lo]
 
+        # The context lock is held only around the native calls, never across a `yield`: a slow or abandoned consumer
+        # must not block other threads of the device.  The session (its slab, the pinned scratch) lives until the
+        # generator is exhausted or closed - use `contextlib.closing(model.generate_stream(...))` or exhaust it.
         with ctx.lock:
             ctx.check(lib.zb_generate_begin(ctx.handle, self._native_model(), C.byref(cache), C.byref(desc), C.byref(gen), stream))
-            try:
-                max_steps = T_delayed - (P + 1)
-                enq = 0
-                while True:
+        try:
+            max_steps = T_delayed - (P + 1)
+            enq = 0
+            while True:
+                piece = None
+                with ctx.lock:
                     # run until the next chunk is final: front (= offset - Q complete frames) >= emitted + chunk + holdback
                     need_front = emitted + chunk_frames + holdback_frames
                     need_steps = min(max_steps, need_front + Q - (P + 1))
                     if need_steps > enq:
-                        ctx.check(lib.zb_generate_steps(gen, need_steps - enq, stream))
+                        torch.ops.zonos_b200.decode_step(gen.value, need_steps - enq, delayed, params.lengths_per_sample)
                         enq = need_steps
                     ctx.check(lib.zb_generate_poll(gen, C.byref(prog), stream))
                     front = int(prog.offset) - Q
-                    if prog.done or enq >= max_steps:
-                        break
-                    hi = min(front - holdback_frames, emitted + chunk_frames)
-                    if hi > emitted:
-                        yield emit(emitted, hi, last=False)
-                        emitted = hi
+                    finished = bool(prog.done) or enq >= max_steps
+                    if not finished:
+                        hi = min(front - holdback_frames, emitted + chunk_frames)
+                        if hi > emitted:
+                            piece = emit(emitted, hi, last=False)
+                            emitted = hi
+                if finished:
+                    break
+                if piece is not None:
+                    yield piece
+            piece = None
+            with ctx.lock:
                 final = self._finalize(delayed, int(prog.offset))
-                if final.shape[-1] > emitted - 0:
-                    valid = final.shape[-1]
-                    if valid > emitted:
-                        ctx_lo = max(0, emitted - halo)
-                        wav = self.autoencoder.decode(final[..., ctx_lo:valid])
-                        yield wav[..., 512 * (emitted - ctx_lo):], final[..., emitted:valid]
-            finally:
+                valid = final.shape[-1]
+                if valid > emitted:
+                    ctx_lo = max(0, emitted - halo)
+                    wav = self.autoencoder.decode(final[..., ctx_lo:valid])
+                    piece = (wav[..., 512 * (emitted - ctx_lo):], final[..., emitted:valid])
+            if piece is not None:
+                yield piece
+        finally:
+            with ctx.lock:
                 lib.zb_generate_end(gen)
 
     def _finalize(self, delayed: torch.Tensor, offset: int) -> torch.Tensor:

@@ -3,7 +3,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, ops  # noqa: F401
 
 
 def sampling_struct(temperature=1.0, top_p=0.0, top_k=0, min_p=0.0, linear=0.0, conf=0.0, quad=0.0,
@@ -26,22 +26,17 @@ def sample_from_logits(logits: torch.Tensor, temperature: float = 1.0, top_p: fl
     assert logits.dim() == 3
     B, Q, V = logits.shape
     lg = logits.contiguous().float()
-    sp = sampling_struct(temperature, top_p, top_k, min_p, linear, conf, quad, repetition_penalty, repetition_penalty_window)
-    win, wsb, wsq, W = None, 0, 0, 0
+    win = None
     if generated_tokens is not None:
         win = generated_tokens.to(torch.int64)
         if win.stride(-1) != 1:
             win = win.contiguous()
-        wsb, wsq, W = win.stride(0), win.stride(1), win.shape[2]
     if q is not None:
         q = q.contiguous().float()
         assert q.shape == lg.shape and q.is_cuda
     if seed is None:
         seed = int(torch.randint(0, 2**62, (1,)).item()) if q is None else 0
-    tokens = torch.empty((B, Q), dtype=torch.int64, device=lg.device)
-    ctx = _lib.context(lg.device)
-    with ctx.lock:
-        ctx.check(ctx.lib.zb_sample_from_logits(ctx.handle, C.byref(sp), _lib.ptr(lg), B, Q, V, _lib.ptr(win), wsb, wsq, W,
-                                                _lib.ptr(q), seed, draw_index, int(apply_logit_bias), _lib.ptr(tokens),
-                                                _lib.stream_ptr(lg.device)))
+    tokens = torch.ops.zonos_b200.sample_update(lg, win, q, [float(temperature), float(top_p), float(min_p), float(linear), float(conf),
+                                                              float(quad), float(repetition_penalty)], int(top_k),
+                                                int(repetition_penalty_window), int(seed), int(draw_index), bool(apply_logit_bias))
     return tokens.unsqueeze(-1)

@@ -3,8 +3,7 @@
 Utterances never interact inside `generate` (rows of different utterances share nothing but the weights), so the
 multi-GPU mode is one process per GPU, a full weight replica each, and NO collective on the decode path: rank g
 takes utterances [g*B/N, (g+1)*B/N).  The only cross-rank traffic is the final gather of the finished codes (a few KB
-per utterance) and, to keep the reference's single-call semantics, the batch-global truncation of
-`zonos/model.py:513-539`, which is re-applied on the gathered batch.
+per utterance), which is aligned to ONE length like a single reference call's batch (`batch_global_align`).
 """
 import torch
 import torch.distributed as dist
@@ -25,11 +24,23 @@ def shard_conditioning(prefix_conditioning: torch.Tensor, batch_size: int, world
     return torch.cat([prefix_conditioning[lo:hi], prefix_conditioning[batch_size + lo:batch_size + hi]], dim=0)
 
 
-def batch_global_truncate(codes: list[torch.Tensor], pad_value: int = 0) -> torch.Tensor:
-    """Per-rank outputs may have different valid lengths (each rank's early exit only sees its own utterances); the
-    reference cuts every utterance of a call at ONE length, the shortest per-rank result is the batch-global bound."""
-    n = min(c.shape[-1] for c in codes)
-    return torch.cat([c[..., :n] for c in codes], dim=0)
+def batch_global_align(codes: list[torch.Tensor], pad_value: int = 512) -> torch.Tensor:
+    """Per-rank outputs may have different lengths: each rank's loop ends when ITS utterances have finished.  A single
+    reference call runs until ALL rows have finished (`zonos/utilities/tensor_ops.py:95`, `.all()`), so its length follows
+    the LONGEST utterance, and an utterance that ended earlier is filled with masked tokens, which the output
+    clean-up turns into 512 (`zonos/model.py:531-535`).  The gathered batch is therefore right-padded with 512 to the
+    longest per-rank result; no utterance is ever cut.  (The reference's last-50-positions EOS scan, `model.py:513-528`,
+    counts EOS over the whole batch and can trim a few trailing frames more than a rank-local scan does; by then the
+    EOS tokens are gone, so that trim is not re-applied here: the sharded result can be a few frames LONGER than the
+    single-call one, never shorter.)"""
+    n = max(c.shape[-1] for c in codes)
+    out = []
+    for c in codes:
+        if c.shape[-1] < n:
+            pad = torch.full((*c.shape[:-1], n - c.shape[-1]), pad_value, dtype=c.dtype, device=c.device)
+            c = torch.cat([c, pad], dim=-1)
+        out.append(c)
+    return torch.cat(out, dim=0)
 
 
 def generate_sharded(generate_fn, prefix_conditioning: torch.Tensor, batch_size: int, audio_prefix_codes: torch.Tensor | None = None,
@@ -52,4 +63,4 @@ def generate_sharded(generate_fn, prefix_conditioning: torch.Tensor, batch_size:
     dist.gather_object(payload, gathered, dst=0, group=group)
     if rank != 0:
         return None
-    return batch_global_truncate([g for g in gathered if g is not None])
+    return batch_global_align([g for g in gathered if g is not None])

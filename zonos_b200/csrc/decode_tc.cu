@@ -76,7 +76,7 @@ struct TcArgs {
   const bf16* emb[16]; int Q, vocab; const int64_t* delayed; int T_delayed;
   bf16 *x, *xn, *q, *ay, *y1, *h; float* ws; float* attn_part; unsigned* pair_cnt;
   unsigned* bar; const zb_loop_state* loop;
-  int stages, bstages, bslot_bytes, nbar, na; float scale;
+  int stages, bstages, bslot_bytes, nbar, na, fc1_direct, l2pf; float scale;
   unsigned long long* timeline;
 };
 
@@ -210,6 +210,24 @@ __device__ __forceinline__ void tc_produce(const TcArgs& a, const TcGemm& g, con
     }
   }
 }
+// L2 prefetch of the CTA's whole unit of a weight matrix, issued one GEMM ahead of the ring: HBM then keeps streaming
+// while the ring (4-6 slots) is full, i.e. during the dump / barrier / epilogue sub-phases, and the ring fills from L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_prefetch(const TcArgs& a, const TcGemm& g, const CUtensorMap* map, int kind) {
+  if (!a.l2pf) return;
+  const Unit u = unit_of(g);
+  for (int j = 0; j < u.kb1 - u.kb0; ++j) {
+    const int kb = unit_kb(u, j);
+    if (kind == G_FC1) {
+      tma_prefetch_2d(map, kb * 64, u.rb * g.RBv);
+      tma_prefetch_2d(map, kb * 64, a.F + u.rb * g.RBv);
+    } else {
+      tma_prefetch_2d(map, kb * 64, u.rb * g.RB);
+    }
+  }
+}
 // the CTA's K/V tiles of one attention phase: slot = K[64 tok][d 0..63] | K[..][d 64..127] | V likewise (8 KB boxes)
 __device__ __forceinline__ void tc_produce_kv(const TcArgs& a, const AttnSched& s, const CUtensorMap* map, unsigned char* ring, uint64_t* full_bar,
                                               uint64_t* empty_bar, int& gst) {
@@ -316,11 +334,47 @@ __device__ __forceinline__ void tc_dump(const TcArgs& a, const TcGemm& g, int ki
   }
 }
 
+// ---- fc1 without a K split: value * silu(gate) straight from tensor memory ------------------------------------------
+// The CTA's accumulator holds value rows (TMEM lanes 0 .. RBv-1) and the gate rows of the SAME features (lanes RBv ..
+// 2 RBv-1) for all activation rows (columns).  Gate values cross from their lanes to the value lanes through shared
+// memory (the activation ring is idle between two GEMMs); no partials, no grid barrier, no second pass over L2.
+__device__ __forceinline__ void tc_epi_silu_direct(const TcArgs& a, const TcGemm& g, const Unit& u, uint32_t tmem, float* sbuf, int cw, int lane) {
+  const int quarter = (cw + 3) & 3, half = cw >> 2;
+  const int ncol = a.Rp / 2, ld = a.Rp + 1;                   // padded rows: consecutive weight rows hit consecutive banks
+  const int lr = quarter * 32 + lane;
+  for (int c0 = 0; c0 < ncol; c0 += 8) {
+    if (half * ncol + c0 >= a.R) break;                       // warp-uniform
+    float v[8];
+    tc_ld8(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * ncol + c0), v);
+    if (lr < 2 * g.RBv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sbuf[lr * ld + half * ncol + c0 + j] = v[j];
+    }
+  }
+  cbar();
+  // (activation row m, feature pair) tasks over all 256 threads: consecutive threads write consecutive features
+  const int hp2 = g.RBv / 2, ctid = cw * 32 + lane;
+  const int nvalid = min(g.RBv, a.F - u.rb * g.RBv);          // features of this block that exist (last block)
+  for (int t = ctid; t < a.R * hp2; t += kCThreads) {
+    const int m = t / hp2, i = (t % hp2) * 2;
+    if (i >= nvalid) continue;
+    float r2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float yv = rbf(sbuf[(i + e) * ld + m]), gg = rbf(sbuf[(g.RBv + i + e) * ld + m]);
+      const float sg = rbf(gg / (1.0f + expf(-gg)));                  // F.silu on bf16: fp32 math, bf16 result
+      r2[e] = __fmul_rn(yv, sg);
+    }
+    *reinterpret_cast<uint32_t*>(a.h + (size_t)m * a.F + (size_t)u.rb * g.RBv + i) = pack_bf16(r2[0], r2[1]);
+  }
+}
+
 // ---- compute-warp side of one GEMM phase ------------------------------------------------------------------------
 struct CState { int gst, nacc; unsigned epoch; unsigned long long* tl; int ti; };
 // debug timeline: stamp slot cs.ti of this CTA's row (only while cs.tl is set: one layer of a step), compute thread 0
 #define TL_STAMP(cs, ctid) do { if ((cs).tl && (ctid) == 0 && (cs).ti < 128) (cs).tl[(cs).ti] = gtime_tc(); ++(cs).ti; } while (0)
-__device__ __forceinline__ void tc_gemm_compute(const TcArgs& a, int kind, uint64_t* b_go, uint64_t* acc_full, uint32_t tmem, CState& cs, int ctid) {
+__device__ __forceinline__ void tc_gemm_compute(const TcArgs& a, int kind, uint64_t* b_go, uint64_t* acc_full, uint32_t tmem, float* gbuf, CState& cs,
+                                                int ctid) {
   const TcGemm& g = a.g[kind];
   const Unit u = unit_of(g);
   if (ctid == 0) mbar_arrive(b_go);                           // (after a grid barrier) release the activation producer
@@ -331,7 +385,8 @@ __device__ __forceinline__ void tc_gemm_compute(const TcArgs& a, int kind, uint6
   ++cs.nacc;
   tc_fence_after();
   TL_STAMP(cs, ctid);                                         // accumulator complete
-  tc_dump(a, g, kind, u, tmem, ctid >> 5, ctid & 31);
+  if (kind == G_FC1 && a.fc1_direct) tc_epi_silu_direct(a, g, u, tmem, gbuf, ctid >> 5, ctid & 31);
+  else tc_dump(a, g, kind, u, tmem, ctid >> 5, ctid & 31);
   tc_fence_before();
 }
 
@@ -339,8 +394,24 @@ __device__ __forceinline__ void tc_gemm_compute(const TcArgs& a, int kind, uint6
 __device__ __forceinline__ void sum_partials(const TcArgs& a, const TcGemm& g, int m, int n0, float (&v)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  for (int ks = 0; ks < g.nks; ++ks) {
-    const float* p = a.ws + ((size_t)ks * a.R + m) * g.Nw + n0;
+  const size_t stride = (size_t)a.R * g.Nw;
+  const float* p = a.ws + (size_t)m * g.Nw + n0;
+  int ks = 0;
+  // four slices per round: the eight loads are in flight together (one L2 round trip instead of four); the additions
+  // keep the slice order
+  for (; ks + 4 <= g.nks; ks += 4, p += 4 * stride) {
+    float4 lo[4], hi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      lo[e] = __ldcg(reinterpret_cast<const float4*>(p + e * stride));
+      hi[e] = __ldcg(reinterpret_cast<const float4*>(p + e * stride + 4));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[0] += lo[e].x; v[1] += lo[e].y; v[2] += lo[e].z; v[3] += lo[e].w; v[4] += hi[e].x; v[5] += hi[e].y; v[6] += hi[e].z; v[7] += hi[e].w;
+    }
+  }
+  for (; ks < g.nks; ++ks, p += stride) {
     const float4 a0 = __ldcg(reinterpret_cast<const float4*>(p)), a1 = __ldcg(reinterpret_cast<const float4*>(p + 4));
     v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
   }
@@ -828,10 +899,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       int gst = 0;
       for (int li = 0; li < a.n_layer; ++li) {
         const TcLayer* L = layers + li;
+        tc_prefetch(a, a.g[G_OUT], &L->map[M_OUT], G_OUT);
         tc_produce(a, a.g[G_QKV], &L->map[M_IN], G_QKV, ring, full_bar, empty_bar, gst);
         tc_produce_kv(a, sched, &L->map[M_KV], ring, full_bar, empty_bar, gst);
+        tc_prefetch(a, a.g[G_FC1], &L->map[M_FC1], G_FC1);
         for (int rep = 0; rep < a.out_proj_repeats; ++rep) tc_produce(a, a.g[G_OUT], &L->map[M_OUT], G_OUT, ring, full_bar, empty_bar, gst);
+        tc_prefetch(a, a.g[G_FC2], &L->map[M_FC2], G_FC2);
         tc_produce(a, a.g[G_FC1], &L->map[M_FC1], G_FC1, ring, full_bar, empty_bar, gst);
+        if (li + 1 < a.n_layer) tc_prefetch(a, a.g[G_QKV], &L[1].map[M_IN], G_QKV);
+        else tc_prefetch(a, a.g[G_HEADS], &acts->map[0], G_HEADS);
         tc_produce(a, a.g[G_FC2], &L->map[M_FC2], G_FC2, ring, full_bar, empty_bar, gst);
       }
       tc_produce(a, a.g[G_HEADS], &acts->map[0], G_HEADS, ring, full_bar, empty_bar, gst);
@@ -874,7 +950,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     const unsigned step0 = *reinterpret_cast<volatile unsigned*>(a.bar + 1);
     CState cs; cs.gst = 0; cs.nacc = 0; cs.epoch = step0 * (unsigned)a.nbar; cs.tl = nullptr; cs.ti = 0;
 #define TC_STAMP() TL_STAMP(cs, ctid)
-#define TC_GEMM(kind) tc_gemm_compute(a, kind, &b_go, &acc_full, tmem, cs, ctid)
+#define TC_GEMM(kind) tc_gemm_compute(a, kind, &b_go, &acc_full, tmem, reinterpret_cast<float*>(bring), cs, ctid)
 #define TC_BARRIER() do { TC_STAMP(); grid_barrier(a, cs.epoch, ctid); TC_STAMP(); } while (0)
     tc_embed(a, layers[0].norm_w, layers[0].norm_b, red, cw, lane, ctid);
     TC_BARRIER();
@@ -905,8 +981,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       // fc1 -> value * silu(gate)
       TC_GEMM(G_FC1);
       TC_BARRIER();
-      tc_epi(a, G_FC1, E_SILU, nullptr, nullptr, cw, lane);
-      TC_BARRIER();
+      if (!a.fc1_direct) {
+        tc_epi(a, G_FC1, E_SILU, nullptr, nullptr, cw, lane);
+        TC_BARRIER();
+      } else {
+        cs.ti += 2;
+      }
       // fc2 + residual, then the next layer's first norm (or the final norm)
       TC_GEMM(G_FC2);
       TC_BARRIER();
@@ -942,7 +1022,7 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct TcPlan {
   TcGemm g[G_COUNT];
-  int Rp, stages, bstages, bslot_bytes, na;
+  int Rp, stages, bstages, bslot_bytes, na, fc1_direct;
   size_t smem, ws_bytes;
 };
 
@@ -983,6 +1063,9 @@ bool tc_plan(const zb_model_desc& d, int R, int grid, TcPlan* p) {
     return false;
   if (d.out_proj_repeats < 1 || d.out_proj_repeats > 2 || (d.out_proj_repeats == 2 && qn != d.d_model)) return false;
   p->ws_bytes = ws;
+  // fc1 epilogue straight from tensor memory: no K split and the staging [2 RBv][Rp + 1] floats fits the activation ring
+  p->fc1_direct = p->g[G_FC1].nks == 1 && (size_t)2 * p->g[G_FC1].RBv * (p->Rp + 1) * 4 <= (size_t)p->bstages * p->bslot_bytes &&
+                  env_int_tc("ZB_TC_FC1_DIRECT", 1);
   const size_t fixed = (size_t)p->bstages * p->bslot_bytes + 1024 /* alignment */;
   const size_t avail = (size_t)227 * 1024 - 2048;           // static shared memory: barriers, attention schedule, reduction scratch
   if (avail < fixed + 2 * (size_t)kSlot) return false;
@@ -1102,7 +1185,8 @@ zb_status zb_launch_decode_tc(zb_ctx* ctx, const zb_model* model, const zb_cache
     const TcArena A = tc_arena(d, p, R, ctx->num_sms, (void*)ab);
     a.x = A.x; a.xn = A.xn; a.y1 = A.y1; a.q = A.q; a.ay = A.ay; a.h = A.h; a.ws = A.ws; a.attn_part = A.attn_part; a.pair_cnt = A.pair_cnt;
   }
-  a.bar = bar; a.loop = loop; a.nbar = 2 + d.n_layer * (7 + 2 * d.out_proj_repeats);
+  a.bar = bar; a.loop = loop; a.fc1_direct = p.fc1_direct; a.l2pf = env_int_tc("ZB_TC_L2PF", 0);   // measured: no gain (the ring, not HBM latency, paces the main loops) and the K/V stream loses L2
+  a.nbar = 2 + d.n_layer * (7 + 2 * d.out_proj_repeats - (p.fc1_direct ? 1 : 0));
   a.stages = p.stages; a.bstages = p.bstages; a.bslot_bytes = p.bslot_bytes; a.na = p.na;
   a.scale = 1.0f / sqrtf((float)d.head_dim); a.timeline = g_tc_timeline;
   ZB_CUDA(ctx, zb_ensure_smem(ctx, decode_tc_kernel, p.smem));

@@ -309,6 +309,30 @@ def test_dac_decode_matches_reference_golden():
     assert err2.max() < 2.5 * noise.max() and err2.mean() < 2.5 * noise.mean(), (err2.max(), err2.mean(), noise.max(), noise.mean())
 
 
+@pytest.mark.parametrize("gain", [0.8, 1.0])
+def test_dac_decode_unsaturated_is_tight(gain):
+    """The golden fixture's random-init decoder (gain 1.3) saturates tanh, which could hide a wrong tap or phase in one
+    small-channel stage.  With smaller weights the decoder stays in its smooth regime (output rms 0.09 / 0.18, |wav| <=
+    0.31, bf16 rounding moves the fp32 result by 0.3 % rms - measured with the oracle), so every layer's error reaches the
+    output: the kernel must agree with the oracle's bf16-autocast emulation to 1 % rms and with the fp32 path to 1.5 %;
+    a misplaced tap, phase, dilation or Snake parameter gives errors of order 1."""
+    from zonos_b200 import DACAutoencoder
+    wd = make_dac_weights(seed=1, gain=gain)
+    codes = torch.randint(0, 1024, (2, 9, 12), generator=torch.Generator().manual_seed(3))
+    wav = DACAutoencoder(wd, device=DEV).decode(codes.to(DEV)).cpu()
+    ref = o_dac.decode(wd, codes)
+    emu = o_dac.decode(wd, codes, autocast_bf16=True)
+    rms = float(ref.pow(2).mean().sqrt())
+    assert rms > 0.05 and float(ref.abs().max()) < 0.5                        # really unsaturated
+    e_emu = float((wav - emu).pow(2).mean().sqrt()) / rms
+    e_ref = float((wav - ref).pow(2).mean().sqrt()) / rms
+    assert e_emu < 0.01 and e_ref < 0.015, (e_emu, e_ref)
+    assert float((wav - emu).abs().max()) < 0.01, float((wav - emu).abs().max())
+    # the pre-tanh signal (tanh is still invertible here): same bound
+    pre, pre_emu = torch.atanh(wav.clamp(-0.999, 0.999)), torch.atanh(emu.clamp(-0.999, 0.999))
+    assert float((pre - pre_emu).pow(2).mean().sqrt()) / float(pre_emu.pow(2).mean().sqrt()) < 0.01
+
+
 def test_dac_decode_properties():
     """Size-independent checks at a realistic length: batch rows independent, a longer utterance shares its interior
     with a shorter one (finite receptive field), output bounded by tanh."""

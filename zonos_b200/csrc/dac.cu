@@ -32,9 +32,17 @@ struct ConvArgs {
   const float* alpha;  // [Cout] or null (identity)
 };
 
+// Snake1d (modeling_dac.py:85-99): x + sin(alpha x)^2 / (alpha + 1e-9), fp32.  sin^2 has period pi: two-term
+// Cody-Waite reduction (exact product k * pi_hi for |k| < 2^11, error ~ k * 1e-15 beyond) + the SFU sine on [-pi/2, pi/2]
+// (abs error 2^-21, far below the bf16 rounding that follows).  sinf()'s slow path (arguments > 1e5, local memory) made
+// the epilogue the bottleneck of the decoder on saturated activations; the reciprocal is IEEE-rounded like torch's.
 __device__ __forceinline__ float snake_f(float x, float alpha) {
-  const float s = sinf(alpha * x);
-  return x + (1.0f / (alpha + 1e-9f)) * (s * s);
+  const float y = alpha * x;
+  const float k = rintf(y * 0.318309886183790672f);
+  float r = fmaf(-k, 3.140625f, y);                            // pi = 3.140625 + 9.67653589793e-4 (hi has 8 significant bits)
+  r = fmaf(-k, 9.67653589793e-4f, r);
+  const float sn = __sinf(r);
+  return x + __frcp_rn(alpha + 1e-9f) * (sn * sn);
 }
 
 constexpr int BM = 64, BN = 64, BK = 32;
@@ -121,7 +129,7 @@ struct ConvTcArgs {
   int BN, stages;
 };
 
-__global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs p) {
+__global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_constant__ ConvTcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem_cv[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
@@ -407,9 +415,16 @@ zb_status run_conv(zb_ctx* ctx, const zb_conv_w& c, const bf16* in, int B, int L
     cuuint32_t box[2] = {64, (cuuint32_t)bn};
     if (zb_status st = make_map(ctx, &p.map_w, c.w, 2, dims, str, box)) return st;
   }
+  // Several CTAs per SM, so that the epilogue of one tile (Snake + stores on 128 threads) overlaps the TMA / MMA main
+  // loops of the others: tensor memory allows 512 / columns CTAs, shared memory is split between them.
   const int a_bytes = 128 * 64 * 2, b_bytes = ((bn * 64 * 2 + 1023) / 1024) * 1024;
-  int stages = (160 * 1024) / (a_bytes + b_bytes);
+  static const int env_ctas = getenv("ZB_DAC_CTAS") ? atoi(getenv("ZB_DAC_CTAS")) : 0;
+  int ctas = bn <= 128 ? 3 : 2;
+  if (env_ctas > 0) ctas = std::min(env_ctas, bn <= 128 ? 4 : 2);
+  const int nk_total = c.taps * (a.in_ld / 64);
+  int stages = ((220 * 1024) / ctas - 1024) / (a_bytes + b_bytes);
   if (stages > 8) stages = 8;
+  if (stages > nk_total) stages = nk_total;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * (a_bytes + b_bytes) + 1024;

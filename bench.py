@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--cond-len", type=int, default=160)
     ap.add_argument("--ref-frames", type=int, default=128, help="frames per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="transformer", choices=["transformer", "hybrid"],
+                    help="headline model: Zonos-v0.1-transformer (configs[1]/[3]) or Zonos-v0.1-hybrid (Mamba2 + attention, configs[2]/[4])")
+    ap.add_argument("--prefix-frames", type=int, default=0, help="synthetic audio-prefix codes per utterance (configs[4]: 258 = 3 s)")
+    ap.add_argument("--no-hybrid", action="store_true", help="skip the hybrid batch-1 leg of the default run")
     ap.add_argument("--no-batch64", action="store_true", help="skip the 64-utterances-per-GPU leg")
     ap.add_argument("--batch64-steps", type=int, default=2)
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the informative reference-torch-on-this-GPU timing")
@@ -52,11 +56,17 @@ def parse():
     return ap.parse_args()
 
 
-def config_dict(args, n_gpus, batch=None):
+def config_dict(args, n_gpus, batch=None, variant=None):
     batch = args.batch if batch is None else batch
-    return {"workload": "Zonos-v0.1-transformer random-init bf16, CFG 2.0, %d utterance(s)/GPU x %d frames (%.1f s) + DAC 44.1 kHz decode"
-                        % (batch, args.frames, args.frames / FRAME_RATE),
-            "baseline_config": "configs[1]" if batch == 1 else ("configs[3]" if batch == 64 else "configs[3]-shaped"),
+    variant = args.variant if variant is None else variant
+    if variant == "hybrid":
+        base = "configs[2]" if batch == 1 and not args.prefix_frames else "configs[4]-shaped"
+    else:
+        base = "configs[1]" if batch == 1 else ("configs[3]" if batch == 64 else "configs[3]-shaped")
+    return {"workload": "Zonos-v0.1-%s random-init bf16, CFG 2.0, %d utterance(s)/GPU x %d frames (%.1f s)%s + DAC 44.1 kHz decode"
+                        % (variant, batch, args.frames, args.frames / FRAME_RATE,
+                           " after a %d-frame audio prefix" % args.prefix_frames if args.prefix_frames else ""),
+            "baseline_config": base, "variant": variant, "prefix_frames": args.prefix_frames,
             "batch_per_gpu": batch, "frames": args.frames, "cond_len": args.cond_len, "cfg_scale": 2.0,
             "sampling": "min_p=0.1, repetition_penalty=3.0 (generate defaults)", "n_layer": args.layers,
             "parallelism": "request-sharded replicas x%d, no data-path collective" % n_gpus,
@@ -74,9 +84,26 @@ def cpu_setup(args):
     from oracle import ref_runner
     dims = dict(TRANSFORMER_DIMS, n_layer=args.layers)
     torch.set_num_threads(os.cpu_count())
+    dacw = make_dac_weights(seed=1)
+    if args.variant == "hybrid":
+        # the reference's hybrid backbone needs mamba_ssm (CUDA-only, not in the image): only the restatement can run here
+        from oracle import dac as o_dac, generate as o_gen
+        from oracle.hybrid import HybridDims, HybridOracle
+        from zonos_b200.synthetic import make_hybrid_weights
+        hd = dict(d_model=2048, n_layer=46, attn_layer_idx=(9, 18, 27, 36, 45), n_heads=16, n_heads_kv=4, d_ff=8192)
+        hw = make_hybrid_weights(**hd, seed=0, heads_scale=8.0)
+        horacle = HybridOracle(hw, HybridDims(**hd), torch.bfloat16)
+        hcond = make_conditioning(2, args.cond_len, 2048)
+
+        def hybrid_step(frames):
+            torch.manual_seed(420)
+            t0 = time.perf_counter()
+            codes = o_gen.generate(horacle, hcond, None, frames, 2.0, 1, dict(min_p=0.1))
+            o_dac.decode(dacw, codes)
+            return codes.shape[2] / FRAME_RATE, time.perf_counter() - t0
+        return "port", hybrid_step
     w = make_backbone_weights(**dims, seed=0, heads_scale=8.0, eos_off=True)
     cond = make_conditioning(2, args.cond_len, dims["d_model"])
-    dacw = make_dac_weights(seed=1)
     if ref_runner.available():
         try:
             model = ref_runner.build_model(dims, w, dacw)
@@ -182,14 +209,37 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     dims = dict(TRANSFORMER_DIMS, n_layer=args.layers)
-    N, Lc = args.frames, args.cond_len
+    N, Lc, P = args.frames, args.cond_len, args.prefix_frames
 
     # every rank builds the same replica (seeded CPU generator) - no weight broadcast needed for synthetic runs
-    w = make_backbone_weights(**dims, seed=0, heads_scale=8.0, eos_off=True)
     dacw = make_dac_weights(seed=1)
-    model = Zonos(ZonosConfig.from_dict(transformer_config_dict(**dims)), autoencoder=DACAutoencoder(dacw, device=dev))
-    model = model.to(dev, torch.bfloat16)
-    model.load_state_dict(w)
+    autoenc = DACAutoencoder(dacw, device=dev)
+
+    def build(variant):
+        """(model, host weights, spec): spec carries what the roofline needs - weight bytes streamed per step, KV bytes per
+        cached token and row, recurrent-state bytes read + written per row and step."""
+        if variant == "transformer":
+            w_ = make_backbone_weights(**dims, seed=0, heads_scale=8.0, eos_off=True)
+            m_ = Zonos(ZonosConfig.from_dict(transformer_config_dict(**dims)), autoencoder=autoenc)
+            n_attn, n_mamba, d_model, hkv = dims["n_layer"], 0, dims["d_model"], dims["n_heads_kv"]
+        else:
+            from zonos_b200 import hybrid_config_dict
+            from zonos_b200.synthetic import make_hybrid_weights
+            hd = dict(d_model=2048, n_layer=46, attn_layer_idx=(9, 18, 27, 36, 45), n_heads=16, n_heads_kv=4, d_ff=8192)
+            w_ = make_hybrid_weights(**hd, seed=0, heads_scale=8.0)
+            w_["fused_heads.weight"][1024] = 0                 # codebook-0 EOS pinned off like eos_off=True: deterministic length
+            m_ = Zonos(ZonosConfig.from_dict(hybrid_config_dict(**hd)), autoencoder=autoenc)
+            n_attn, n_mamba, d_model, hkv = len(hd["attn_layer_idx"]), hd["n_layer"] - len(hd["attn_layer_idx"]), hd["d_model"], hd["n_heads_kv"]
+        m_ = m_.to(dev, torch.bfloat16)
+        m_.load_state_dict(w_)
+        w_bytes = 2 * sum(v.numel() for k, v in w_.items() if k.startswith("backbone.") or k.startswith("fused_heads"))
+        d_inner = 2 * d_model
+        state = n_mamba * 2 * 2 * ((d_inner // 64) * 64 * 128 + (d_inner + 2 * 128) * 4)    # SSM state + conv window, read + write, bf16
+        spec = {"variant": variant, "w_bytes": w_bytes, "kv_tok": n_attn * 2 * hkv * 128 * 2, "state_bytes_per_row": state,
+                "d_model": d_model, "n_layer": n_attn + n_mamba, "hybrid": variant == "hybrid"}
+        return m_, w_, spec
+
+    model, w, spec0 = build(args.variant)
     ctx = model._ctx()
     stream = torch.cuda.current_stream(dev)
     peak, peak_src = measured_peaks()
@@ -199,21 +249,29 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def measure(B, steps, warmup, with_clocks):
+    def measure(model, spec, B, steps, warmup, with_clocks):
         """One leg: `steps` passes (prefill + N frames + DAC decode) of B utterances per GPU.  value = inputs resident in
-        HBM; e2e = pinned host conditioning in, host waveform out, both copies inside the timed region."""
-        cond_host = make_conditioning(2 * B, Lc, dims["d_model"], seed=1234 + rank).pin_memory()
+        HBM; e2e = pinned host conditioning (and prefix codes) in, host waveform out, all copies inside the timed region."""
+        cond_host = make_conditioning(2 * B, Lc, spec["d_model"], seed=1234 + rank).pin_memory()
         cond_dev = cond_host.to(dev)
-        wav_host = torch.empty((B, 1, 512 * N), dtype=torch.float32).pin_memory()
+        prefix_host = prefix_dev = None
+        if P:
+            prefix_host = torch.randint(0, 1024, (B, 9, P), generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+            prefix_dev = prefix_host.to(dev)
+        wav_host = torch.empty((B, 1, 512 * (P + N)), dtype=torch.float32).pin_memory()
+
+        def gen(c, pfx, n_frames, seed):
+            return model.generate(c, pfx, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
 
         def step_device(seed):
-            codes = model.generate(cond_dev, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
+            codes = gen(cond_dev, prefix_dev, N, seed)
             wav = model.autoencoder.decode(codes)
             return codes, wav
 
         def step_e2e(seed):
             c = cond_host.to(dev, non_blocking=True)                       # H2D inside the timed region
-            codes = model.generate(c, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=seed)
+            pfx = prefix_host.to(dev, non_blocking=True) if P else None
+            codes = gen(c, pfx, N, seed)
             wav = model.autoencoder.decode(codes)
             wav_host[..., : wav.shape[-1]].copy_(wav, non_blocking=True)   # D2H of the result
             torch.cuda.current_stream(dev).synchronize()
@@ -227,7 +285,7 @@ def run_b200(args):
             frames = 0
             for i in range(K):
                 codes, _ = fn(1000 + i)
-                frames += codes.shape[0] * codes.shape[2]
+                frames += codes.shape[0] * (codes.shape[2] - P)            # NEW audio only: the prefix was given
             e1.record(stream)
             torch.cuda.synchronize(dev)
             ms = e0.elapsed_time(e1)
@@ -260,12 +318,12 @@ def run_b200(args):
         roof = breakdown = None
         if rank == 0:
             def time_generate(n_frames, reps=2):
-                model.generate(cond_dev, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=5)
+                gen(cond_dev, prefix_dev, n_frames, 5)
                 torch.cuda.synchronize(dev)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
                 for r_ in range(reps):
-                    c_ = model.generate(cond_dev, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=6 + r_)
+                    c_ = gen(cond_dev, prefix_dev, n_frames, 6 + r_)
                 e1.record(stream)
                 torch.cuda.synchronize(dev)
                 return e0.elapsed_time(e1) / reps, c_
@@ -283,21 +341,22 @@ def run_b200(args):
             e1.record(stream)
             torch.cuda.synchronize(dev)
             dac_ms = e0.elapsed_time(e1) / 3
-            per_layer = (dims["n_heads"] + 2 * dims["n_heads_kv"]) * 128 * dims["d_model"] + dims["d_model"] ** 2 \
-                + 3 * dims["d_ff"] * dims["d_model"]
-            w_bytes = 2 * (dims["n_layer"] * per_layer + 9 * 1025 * dims["d_model"])
-            kv_tok = dims["n_layer"] * 2 * dims["n_heads_kv"] * 128 * 2
-            mean_s = Lc + 1 + (n_small + N + 16) / 2
-            step_bytes = w_bytes + 2 * B * mean_s * kv_tok + 2 * B * kv_tok + B * (9 * dims["d_model"] * 2 + 9 * 1025 * 4)
+            w_bytes, kv_tok = spec["w_bytes"], spec["kv_tok"]
+            mean_s = Lc + P + 1 + (n_small + N + 16) / 2
+            step_bytes = w_bytes + 2 * B * mean_s * kv_tok + 2 * B * kv_tok + 2 * B * spec["state_bytes_per_row"] \
+                + B * (9 * spec["d_model"] * 2 + 9 * 1025 * 4)
             achieved = step_bytes / (step_ms * 1e-3) / 1e9
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tpath):
+            if os.path.exists(tpath) and not spec["hybrid"] and not P:
                 traffic = json.load(open(tpath)).get("batch%d_decode_step_dram_bytes_per_launch" % B)
-            if 2 * B <= 4:
-                kname = "decode_step_kernel<R=%d> (persistent FFMA2 consumer: embed + %d layers + heads, one launch per frame) + sample kernel" % (2 * B, dims["n_layer"])
+            if spec["hybrid"]:
+                kname = "decode step of the hybrid stack as ONE CUDA graph of %d layers (gemv3_kernel / gemm_tc_kernel Linears, mamba_scan_kernel, " \
+                        "gated_norm_kernel, attn_kernel) + sample kernel, R=%d rows" % (spec["n_layer"], 2 * B)
+            elif 2 * B <= 4:
+                kname = "decode_step_kernel<R=%d> (persistent FFMA2 consumer: embed + %d layers + heads, one launch per frame) + sample kernel" % (2 * B, spec["n_layer"])
             else:
-                kname = "decode_tc_kernel, R=%d rows (persistent tcgen05/TMEM consumer + mma.sync attention: embed + %d layers + heads, one launch per frame) + sample kernel" % (2 * B, dims["n_layer"])
+                kname = "decode_tc_kernel, R=%d rows (persistent tcgen05/TMEM consumer + mma.sync attention: embed + %d layers + heads, one launch per frame) + sample kernel" % (2 * B, spec["n_layer"])
             roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src, "us_per_launch": step_ms * 1e3, "algorithmic_bytes_per_launch": step_bytes,
                     "how": "slope of generate() time between %d and %d frames (CUDA events)" % (n_small, N)}
@@ -309,11 +368,11 @@ def run_b200(args):
                 "clocks": clock_info, "roofline": roof, "breakdown_ms": breakdown, "cond_dev": cond_dev}
 
     B = args.batch
-    head = measure(B, args.steps, max(args.warmup, 3), True)
+    head = measure(model, spec0, B, args.steps, max(args.warmup, 3), True)
     cond_dev = head.pop("cond_dev")
     roof = head["roofline"]
 
-    if rank == 0 and roof is not None and 2 * B <= 8:
+    if rank == 0 and roof is not None and 2 * B <= 8 and args.variant == "transformer":
         # stand-alone norm2 + fc1 + SiLU GEMV (55 % of the weight bytes) in a C-side launch loop over all layers
         native = model._native_model()
         sp = _lib.stream_ptr(dev)
@@ -340,7 +399,7 @@ def run_b200(args):
         for i in range(5):
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            gen_it = model.generate_stream(cond_dev, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=40 + i)
+            gen_it = model.generate_stream(cond_dev, None, max_new_tokens=N, cfg_scale=2.0, batch_size=B, sampling_params=dict(min_p=0.1), seed=40 + i)
             wav0, _ = next(gen_it)
             wav0.cpu()
             samples.append((time.perf_counter() - t0) * 1e3)
@@ -353,8 +412,9 @@ def run_b200(args):
 
     # ---- the other half of the metric: 64 utterances per GPU (BASELINE.json configs[3]); every rank runs it ----
     batch64 = None
-    if B == 1 and not args.no_batch64:
-        b64 = measure(64, max(1, args.batch64_steps), 1, False)
+    default_run = B == 1 and args.variant == "transformer" and not P
+    if default_run and not args.no_batch64:
+        b64 = measure(model, spec0, 64, max(1, args.batch64_steps), 1, False)
         b64.pop("cond_dev")
         if rank == 0:
             batch64 = {"metric": METRIC, "value": b64["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": max(1, args.batch64_steps), "warmup": 1,
@@ -362,9 +422,26 @@ def run_b200(args):
                        "gpu_launches": b64["launches"], "roofline": b64["roofline"], "breakdown_ms": b64["breakdown_ms"],
                        "config": config_dict(args, n_gpus, 64), "target_audio_s_per_s_per_box_of_8": 3000.0}
 
+    # ---- BASELINE.json configs[2]: the hybrid (Mamba2 + attention) variant at batch 1; every rank runs it ----
+    hybrid = None
+    if default_run and not args.no_hybrid:
+        hm, hw, hspec = build("hybrid")
+        del hw
+        hy = measure(hm, hspec, 1, 2, 1, False)
+        hy.pop("cond_dev")
+        if rank == 0:
+            hybrid = {"metric": METRIC, "value": hy["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": 2, "warmup": 1, "ms_per_step": hy["ms_per_step"],
+                      "e2e": hy["e2e"], "gpu_launches": hy["launches"], "roofline": hy["roofline"], "breakdown_ms": hy["breakdown_ms"],
+                      "config": config_dict(args, n_gpus, 1, "hybrid"),
+                      "note": "parity of this variant is pinned by oracle/hybrid.py and transformers' Mamba2Mixer only (the reference's "
+                              "hybrid backbone needs mamba_ssm, which is not in the image); layer count / attention positions are the "
+                              "assumption of configs/zonos_v0.1_hybrid.json"}
+        del hm
+        torch.cuda.empty_cache()
+
     # ---- informative: the reference's own torch path on THIS GPU (eager; SURVEY K1/K2/K16 bars), bounded sample ----
     ref_gpu = None
-    if rank == 0 and not args.no_ref_gpu and B == 1:
+    if rank == 0 and not args.no_ref_gpu and default_run:
         try:
             from oracle import ref_runner
             if ref_runner.available():
@@ -397,7 +474,8 @@ def run_b200(args):
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": config_dict(args, n_gpus), "frames_per_second": head["frames_per_second"],
                 "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"], "roofline": roof,
-                "breakdown_ms": head["breakdown_ms"], "ttfa": ttfa, "batch64": batch64, "reference_gpu_eager": ref_gpu, "cpu_baseline": cpu}
+                "breakdown_ms": head["breakdown_ms"], "ttfa": ttfa, "batch64": batch64, "hybrid_batch1": hybrid, "reference_gpu_eager": ref_gpu,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -412,6 +412,74 @@ def test_hybrid_generate_matches_oracle():
         assert torch.equal(codes.cpu(), ref)
 
 
+def test_hybrid_rms_norm_checkpoint_layout():
+    """A hybrid checkpoint trained with rms_norm=true has weight-only norms (mamba_ssm RMSNorm): the state dict must load
+    without `.bias` keys and the kernels must take the RMS path (zonos/backbone/_mamba_ssm.py:18-40)."""
+    from oracle.hybrid import HybridDims, HybridOracle
+    from zonos_b200 import Zonos, ZonosConfig, hybrid_config_dict
+    from zonos_b200.synthetic import HYBRID_TINY_DIMS, make_hybrid_weights
+    w = {k: v for k, v in make_hybrid_weights(**HYBRID_TINY_DIMS, seed=3).items() if not (k.endswith(".bias") and "norm" in k)}
+    m = Zonos(ZonosConfig.from_dict(hybrid_config_dict(**HYBRID_TINY_DIMS, rms_norm=True))).to(DEV, torch.bfloat16)
+    assert not any(k.endswith(".bias") and "norm" in k for k in m.state_dict())
+    m.load_state_dict(w)                                     # strict: no missing / unexpected keys
+    oracle = HybridOracle(w, HybridDims(**HYBRID_TINY_DIMS, rms_norm=True), torch.bfloat16)
+    R, D = 2, 512
+    g = torch.Generator().manual_seed(6)
+    params, st = m.setup_cache(R, 24), oracle.allocate(R, 24)
+    for T in (7, 1, 1):
+        x = torch.randn(R, T, D, generator=g).bfloat16()
+        got = m.backbone(x.to(DEV), params).float().cpu()
+        ref = oracle.forward(x, st).float()
+        assert (got - ref).abs().max().item() < 0.08
+        params.seqlen_offset += T; params.lengths_per_sample += T
+        st.seqlen_offset += T; st.lengths += T
+
+
+def test_hybrid_mamba_layer_matches_transformers_mixer_directly():
+    """Second opinion that does not go through oracle/hybrid.py: ONE Mamba2 block on the GPU (in_proj -> causal conv1d ->
+    selective scan -> gated RMSNorm -> out_proj, prefill then single-token steps on the carried conv / SSM state) against
+    `transformers`' pure-PyTorch `Mamba2Mixer.torch_forward` run in fp32 on the whole sequence (the recurrence is causal,
+    so step k must equal position T + k of the one-shot result).  Same bf16-representable parameters on both sides."""
+    import torch.nn.functional as F
+    from transformers.models.mamba2.configuration_mamba2 import Mamba2Config
+    from transformers.models.mamba2.modeling_mamba2 import Mamba2Mixer
+    from zonos_b200 import Zonos, ZonosConfig, hybrid_config_dict
+    D, R, T, K = 512, 2, 9, 3
+    cfg = Mamba2Config(hidden_size=D, state_size=128, conv_kernel=4, expand=2, head_dim=64, num_heads=16, n_groups=1, rms_norm=True,
+                       use_bias=False, use_conv_bias=True, chunk_size=4, layer_norm_epsilon=1e-5)
+    torch.manual_seed(0)
+    mixer = Mamba2Mixer(cfg, layer_idx=0).float().eval()
+    with torch.no_grad():
+        mixer.A_log.copy_(torch.log(1 + 15 * torch.rand(16)))
+        mixer.dt_bias.copy_(torch.randn(16) * 0.5)
+        mixer.D.copy_(torch.rand(16) + 0.5)
+        mixer.norm.weight.copy_(1 + 0.1 * torch.randn(1024))
+        for p_ in mixer.parameters():
+            p_.copy_(p_.bfloat16().float())
+    dims = dict(d_model=D, n_layer=1, attn_layer_idx=(), n_heads=4, n_heads_kv=2, d_ff=1024)
+    model = Zonos(ZonosConfig.from_dict(hybrid_config_dict(**dims))).to(DEV, torch.bfloat16).eval()
+    g = torch.Generator().manual_seed(1)
+    nw, nb = (1 + 0.1 * torch.randn(D, generator=g)).bfloat16(), (0.05 * torch.randn(D, generator=g)).bfloat16()
+    fw, fb = (1 + 0.1 * torch.randn(D, generator=g)).bfloat16(), (0.05 * torch.randn(D, generator=g)).bfloat16()
+    sd = model.state_dict()
+    sd.update({"backbone.layers.0.mixer." + k: v.detach().bfloat16() for k, v in mixer.state_dict().items()})
+    sd.update({"backbone.layers.0.norm.weight": nw, "backbone.layers.0.norm.bias": nb, "backbone.norm_f.weight": fw, "backbone.norm_f.bias": fb})
+    model.load_state_dict(sd)
+    x = torch.randn(R, T + K, D, generator=g).bfloat16()
+    with torch.no_grad():
+        h = F.layer_norm(x.float(), (D,), nw.float(), nb.float(), 1e-5)
+        ref = F.layer_norm(x.float() + mixer.torch_forward(h), (D,), fw.float(), fb.float(), 1e-5)
+    params = model.setup_cache(R, T + K)
+    got = [model.backbone(x[:, :T].to(DEV), params).float().cpu()]
+    params.seqlen_offset += T; params.lengths_per_sample += T
+    for k in range(K):
+        got.append(model.backbone(x[:, T + k:T + k + 1].to(DEV), params).float().cpu())
+        params.seqlen_offset += 1; params.lengths_per_sample += 1
+    got = torch.cat(got, dim=1)
+    err = (got - ref).abs().max().item()
+    assert err < 0.08, err                                   # bf16 activations against an fp32 run (outputs are O(1) after the final norm)
+
+
 # ------------------------------------------------------------------------------ full size -------
 @pytest.fixture(scope="module")
 def full_model():

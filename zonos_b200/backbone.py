@@ -67,15 +67,26 @@ class _Mamba2Mixer(nn.Module):
         self.out_proj = nn.Linear(self.d_inner, d_model, bias=False)
 
 
+def _make_norm(cfg: BackboneConfig, rms: bool) -> nn.Module:
+    """Parameter holder of a block norm: LayerNorm (weight + bias) or, for hybrid checkpoints trained with rms_norm=true,
+    mamba_ssm's RMSNorm (weight only - such a state dict has no `.bias` keys)."""
+    return _Weight(cfg.d_model) if rms else nn.LayerNorm(cfg.d_model, eps=cfg.norm_epsilon)
+
+
+def _bias_ptr(norm: nn.Module):
+    b = getattr(norm, "bias", None)
+    return b.data_ptr() if b is not None else None
+
+
 class _Block(nn.Module):
-    def __init__(self, cfg: BackboneConfig, is_attention: bool = True):
+    def __init__(self, cfg: BackboneConfig, is_attention: bool = True, rms: bool = False):
         super().__init__()
         self.is_attention = is_attention
-        self.norm = nn.LayerNorm(cfg.d_model, eps=cfg.norm_epsilon)
+        self.norm = _make_norm(cfg, rms)
         if is_attention:
             heads, heads_kv = cfg.attn_cfg["num_heads"], cfg.attn_cfg["num_heads_kv"]
             self.mixer = _Mixer(cfg.d_model, heads, heads_kv, cfg.d_model // heads)
-            self.norm2 = nn.LayerNorm(cfg.d_model, eps=cfg.norm_epsilon)
+            self.norm2 = _make_norm(cfg, rms)
             self.mlp = _MLP(cfg.d_model, cfg.attn_mlp_d_intermediate)
         else:
             assert cfg.d_intermediate == 0, "Mamba2 layers with an MLP (d_intermediate > 0) are not supported"
@@ -121,8 +132,11 @@ class B200ZonosBackbone(nn.Module):
         if self.hybrid:
             assert config.ssm_cfg.get("layer", "Mamba2") == "Mamba2", "only Mamba2 SSM layers are supported"
         attn = set(config.attn_layer_idx) if self.hybrid else set(range(config.n_layer))
-        self.layers = nn.ModuleList(_Block(config, i in attn) for i in range(config.n_layer))
-        self.norm_f = nn.LayerNorm(config.d_model, eps=config.norm_epsilon)
+        # zonos/backbone/_torch.py ignores rms_norm (LayerNorm always); the mamba_ssm blocks of the hybrid
+        # variant honour it (zonos/backbone/_mamba_ssm.py:18-40 -> create_block(rms_norm=...))
+        rms = self.hybrid and bool(config.rms_norm)
+        self.layers = nn.ModuleList(_Block(config, i in attn, rms) for i in range(config.n_layer))
+        self.norm_f = _make_norm(config, rms)
         # Reference quirks kept as switches.  Transformer variant = zonos/backbone/_torch.py: out_proj applied
         # twice, interleaved-pair RoPE with an fp32 table, LayerNorm.  Hybrid variant = mamba_ssm blocks
         # (zonos/backbone/_mamba_ssm.py): out_proj once, rotate-half RoPE with cos/sin cached in bf16, norm per `rms_norm`.
@@ -170,10 +184,10 @@ class B200ZonosBackbone(nn.Module):
         for i, blk in enumerate(self.layers):
             L = layers[i]
             L.kind = 0 if blk.is_attention else 1
-            L.norm_w, L.norm_b = blk.norm.weight.data_ptr(), blk.norm.bias.data_ptr()
+            L.norm_w, L.norm_b = blk.norm.weight.data_ptr(), _bias_ptr(blk.norm)
             L.in_proj, L.out_proj = blk.mixer.in_proj.weight.data_ptr(), blk.mixer.out_proj.weight.data_ptr()
             if blk.is_attention:
-                L.norm2_w, L.norm2_b = blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr()
+                L.norm2_w, L.norm2_b = blk.norm2.weight.data_ptr(), _bias_ptr(blk.norm2)
                 L.fc1, L.fc2 = blk.mlp.fc1.weight.data_ptr(), blk.mlp.fc2.weight.data_ptr()
             else:
                 mm = blk.mixer
@@ -191,7 +205,7 @@ class B200ZonosBackbone(nn.Module):
         d.rope_interleaved, d.out_proj_repeats = int(self.rope_interleaved), self.out_proj_repeats
         d.norm_eps, d.rope_len, d.rope_table = cfg.norm_epsilon, ROPE_TABLE_LEN, rope.data_ptr()
         d.layers = layers
-        d.norm_f_w, d.norm_f_b = self.norm_f.weight.data_ptr(), self.norm_f.bias.data_ptr()
+        d.norm_f_w, d.norm_f_b = self.norm_f.weight.data_ptr(), _bias_ptr(self.norm_f)
         emb_arr = None
         if embeddings:
             emb_arr = (C.c_void_p * len(embeddings))(*[e.data_ptr() for e in embeddings])

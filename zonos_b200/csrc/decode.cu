@@ -1764,7 +1764,10 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
       if (zb_status st = launch_gemv<PRO_NORM, EPI_QKV>(ctx, a, stream)) return st;
     }
     // 2. attention over the paged cache
-    {
+    static const int pf_mma = env_int("ZB_PREFILL_MMA", 1);
+    if (T > 1 && pf_mma && zb_attn_prefill_supported(d)) {
+      if (zb_status st = zb_launch_attn_prefill(ctx, d, cache, s.q, kv_layer, s.attn_y, R, T, stream)) return st;
+    } else {
       AttnArgs at;
       memset(&at, 0, sizeof(at));
       at.q = s.q; at.kv_layer = kv_layer; at.lengths = cache->lengths; at.page_table = cache->page_table;

@@ -81,6 +81,11 @@ zb_status zb_tc_table_build(zb_ctx* ctx, const zb_model* model, const zb_cache* 
 zb_status zb_launch_decode_tc(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const void* table_dev, unsigned* bar, void* arena, int R,
                               float cfg_scale, float* logits, const int64_t* delayed, int T_delayed, const zb_loop_state* loop, cudaStream_t stream);
 
+// causal attention for T > 1 tokens per row on mma.sync tiles (attn_prefill.cu)
+bool zb_attn_prefill_supported(const zb_model_desc& d);
+zb_status zb_launch_attn_prefill(zb_ctx* ctx, const zb_model_desc& d, const zb_cache* cache, const bf16* q, const bf16* kv_layer, bf16* y, int R, int T,
+                                 cudaStream_t stream);
+
 // ---- tcgen05 GEMM (gemm_tc.cu): Y[M,N] = X[M,K] W[N,K]^T with fused epilogue ----
 struct zb_gemm_tc {
   const bf16* W = nullptr; const bf16* x = nullptr; long long ldx = 0; int M = 0, N = 0, K = 0;

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--time", action="store_true", help="time generate() with CUDA events, both paths")
     ap.add_argument("--no-compare", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="print the phase timeline of CTA 0, layer 1 (last step)")
+    ap.add_argument("--mega", action="store_true", help="compare the two consumers of the B <= 2 persistent kernel (ZB_MEGA_TC=1 tcgen05 / 0 FFMA2) instead")
     args = ap.parse_args()
 
     from helpers import build_b200_model, oracle_dims, q_stream_from_seed
@@ -73,7 +74,10 @@ def main():
         q = q_stream_from_seed(77, N + 9, B) if N <= 64 else None
         res = {}
         for tc in ((1,) if args.no_compare else (1, 0)):
-            os.environ["ZB_DECODE_TC"] = "2" if tc else "0"
+            if args.mega:
+                os.environ["ZB_MEGA_TC"] = "1" if tc else "0"
+            else:
+                os.environ["ZB_DECODE_TC"] = "2" if tc else "0"
             trace = {}
             try:
                 codes = model.generate(cond.to(dev), max_new_tokens=N, batch_size=B, q_stream=q, seed=5, trace=trace if N <= 64 else None)
@@ -113,7 +117,34 @@ def main():
             line += f" | vs oracle: same-history logits max {max(worst):.4f} per call {[round(v, 3) for v in worst[:8]]} forked {forks[-1]}/{B} codes_equal={same}"
         print(line, flush=True)
 
-    if args.timeline:
+    if args.timeline and args.mega:
+        import ctypes as C
+        lib = C.CDLL(_lib.LIB_PATH)
+        lib.zb_debug_timeline.argtypes = [C.c_void_p]
+        for tc in (1, 0):
+            os.environ["ZB_MEGA_TC"] = str(tc)
+            buf = torch.zeros(256, dtype=torch.int64, device=dev)
+            lib.zb_debug_timeline(C.c_void_p(buf.data_ptr()))
+            B = args.batch[-1]
+            cond = make_conditioning(2 * B, args.cond_len, dims["d_model"], seed=9)
+            model.generate(cond.to(dev), max_new_tokens=args.frames, batch_size=B, seed=5)
+            torch.cuda.synchronize()
+            lib.zb_debug_timeline(C.c_void_p(0))
+            t = buf.cpu().double()
+            # stamps of CTA 0: [0] start, [1] embed done, then per layer and phase (in_proj, attention, out x repeats, fc1, fc2): inputs ready, work done
+            names = ["in_proj", "attention", "out1", "out2", "fc1", "fc2"]
+            li = 5
+            base = 2 + li * 12
+            print(f"ZB_MEGA_TC={tc}: CTA 0, layer {li} (us): phase = wait for inputs + work")
+            prev = float(t[base - 1])
+            tot = 0.0
+            for i, nme in enumerate(names):
+                ready, done = float(t[base + 2 * i]), float(t[base + 2 * i + 1])
+                print(f"   {nme:10s} wait {1e-3 * (ready - prev):6.2f}  work {1e-3 * (done - ready):6.2f}")
+                tot += done - prev
+                prev = done
+            print(f"   layer total {1e-3 * tot:.2f} us")
+    elif args.timeline:
         import ctypes as C
         lib = _lib.load()
         buf = torch.zeros(148 * 128, dtype=torch.int64, device=dev)

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "zb_launch_count": (c_int64, [c_void_p]),
     "zb_model_create": (c_int32, [c_void_p, C.POINTER(zb_model_desc), C.POINTER(c_void_p)]),
     "zb_model_destroy": (c_int32, [c_void_p]),
+    "zb_model_weights_changed": (c_int32, [c_void_p]),
     "zb_embed_codes": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "zb_backbone_forward": (c_int32, [c_void_p, c_void_p, C.POINTER(zb_cache), c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "zb_heads_cfg": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p]),

@@ -143,6 +143,7 @@ class B200ZonosBackbone(nn.Module):
         self.out_proj_repeats = 1 if self.hybrid else 2
         self.rope_interleaved = not self.hybrid
         self._handles = {}        # key -> (zb_model handle, keepalive)
+        self._versions = {}       # key -> parameter versions the handle has seen
         self._tables = None       # (embeddings, heads, n_codebooks, head_vocab) registered by the owning Zonos
         self._rope = None
         self._cache: PagedKVCache | None = None
@@ -167,7 +168,13 @@ class B200ZonosBackbone(nn.Module):
             embeddings, heads, n_codebooks, head_vocab = self._tables
         key = self._weights_key() + tuple(e.data_ptr() for e in (embeddings or [])) + ((heads.data_ptr(),) if heads is not None else ())
         hit = self._handles.get(key)
+        # torch bumps a tensor's version on every in-place write (load_state_dict, optimizer steps): same pointers, new
+        # values - the library must rebuild what it derived from the weights (zb_model_weights_changed)
+        versions = tuple(p._version for p in self.parameters())
         if hit is not None:
+            if self._versions.get(key) != versions:
+                _lib.load().zb_model_weights_changed(hit[0])
+                self._versions[key] = versions
             return hit[0]
         cfg = self.config
         ctx = _lib.context(p0.device)
@@ -215,6 +222,7 @@ class B200ZonosBackbone(nn.Module):
         with ctx.lock:
             ctx.check(ctx.lib.zb_model_create(ctx.handle, C.byref(d), C.byref(h)))
         self._handles[key] = (h, (rope, layers, emb_arr))
+        self._versions[key] = versions
         return h
 
     def __del__(self):

@@ -128,6 +128,10 @@ zb_status zb_model_create(zb_ctx* ctx, const zb_model_desc* desc, zb_model** out
 }
 
 zb_status zb_model_destroy(zb_model* model) { delete model; return ZB_OK; }
+zb_status zb_model_weights_changed(zb_model* model) {
+  if (model) model->tcw_valid = false;                       // derived copies are rebuilt by the next generate session
+  return ZB_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 zb_status zb_embed_codes(zb_ctx* ctx, const zb_model* model, const int64_t* codes, int64_t stride_b, int64_t stride_q,
@@ -309,7 +313,7 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
     if (g->mega) {
       g->mega_layers = base + o_layers; g->mega_bar = (unsigned*)(base + o_bar); g->mega_arena = (uint32_t*)(base + o_arena);
       std::vector<unsigned char> hb(table_bytes);
-      if (zb_status st = g->tc ? zb_tc_table_build(ctx, model, cache, R, g->mega_arena, hb.data()) : zb_mega_layers_build(ctx, model, cache, hb.data())) return fail(st);
+      if (zb_status st = g->tc ? zb_tc_table_build(ctx, model, cache, R, g->mega_arena, hb.data()) : zb_mega_layers_build(ctx, model, cache, hb.data(), s)) return fail(st);
       if (sl.layers != hb || sl.layers_off != o_layers) {  // same model and cache as the slab's last session: already there
         sl.layers = hb; sl.layers_off = o_layers;
         G_CUDA(cudaMemcpyAsync(g->mega_layers, sl.layers.data(), hb.size(), cudaMemcpyHostToDevice, s));

@@ -172,21 +172,25 @@ __global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_con
         tma_load_2d(sa + a_bytes, &p.map_w, c0, tap * a.N + n0, &full_bar[s]);
       }
     }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, BN);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % p.stages;
-        mbar_wait(&full_bar[s], (kb / p.stages) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
-        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+  } else if (warp_id_uniform() == 5) {
+    // ===== MMA issuer: the whole warp walks the ring on uniform values, one elected lane issues (see elect_one) =====
+    const uint32_t idesc = make_idesc(128, BN);
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % p.stages;
+      mbar_wait(&full_bar[s], (kb / p.stages) & 1);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+      const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+      if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) tc_mma(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
-        tc_commit(&empty_bar[s]);
+        for (int kk = 0; kk < 4; ++kk)                    // UMMA K = 16 bf16 = 32 bytes: advance the start address
+          tc_mma(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+        tc_commit(&empty_bar[s]);                        // frees the smem slot when these MMAs retire
       }
-      tc_commit(&tmem_full_bar);
+      __syncwarp();
     }
+    if (elect_one()) tc_commit(&tmem_full_bar);          // accumulator complete
+    __syncwarp();
   } else {
     // ===== epilogue: lane <-> GEMM row j (time), 16 output columns per TMEM read =====
     mbar_wait(&tmem_full_bar, 0);

@@ -10,7 +10,7 @@
 
 #include <algorithm>
 
-#include "internal.h"
+#include "tc.cuh"
 
 namespace {
 
@@ -704,7 +704,17 @@ __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
 // out_proj is applied twice by the reference (_torch.py:419-420): its slice is held in the ring between the two
 // passes, so it is read from HBM once.
 // ================================================================================================================
-struct MegaLayer { const bf16 *norm_w, *norm_b, *in_proj, *out_proj, *norm2_w, *norm2_b, *fc1, *fc2; bf16* kv_layer; };
+struct MegaLayer {
+  const bf16 *norm_w, *norm_b, *in_proj, *out_proj, *norm2_w, *norm2_b, *fc1, *fc2; bf16* kv_layer;
+  const bf16 *in_t, *out_t, *fc1_t, *fc2_t;                   // the same matrices re-laid out for the tcgen05 consumer (see MegaTcGeo)
+};
+// tcgen05 consumer: a matrix [N, K] is cut into units of RB weight rows (a multiple of 8; fc1: RBv value rows followed by
+// the RBv gate rows of the same features), unit u belongs to CTA u.  K is cut into S segments of Ks = K / S elements and
+// the unit is stored as Ks/64 consecutive tiles of [S * RB rows][64 k]: tile row s * RB + r holds W[row r][s * Ks + 64 t ..]
+// ("segment-diagonal", see mega_consume_tc), in the 128-byte-swizzle shared-memory image the UMMA descriptor reads.  A
+// unit is ONE contiguous run of RB * K * 2 bytes that 1-D bulk copies move through the ring, kps tiles per 32 KB stage.
+struct MegaTcGeo { int RB, RBv, nunits, kps, S; };
+enum { TG_QKV = 0, TG_OUT = 1, TG_FC1 = 2, TG_FC2 = 3, TG_HEADS = 4, TG_COUNT = 5 };
 // what a thread's in_proj epilogue item needs besides the dot products: position, RoPE cos/sin, KV page.  The same in
 // every layer of a step, so it is fetched once per step (three dependent global loads otherwise trail every in_proj)
 struct MegaQkvPre { int pos, page; float2 cs; bool valid; };
@@ -724,9 +734,12 @@ struct MegaArgs {
   int ring_stages, part_bytes, evict_first;
   unsigned long long* timeline;   // debug: globaltimer stamps of CTA 0 (2 per phase: inputs ready, work done)
   unsigned long long* steplog;    // debug: [2*step] start, [2*step+1] end of every step (CTA 0)
+  // tcgen05 consumer (decode_step_kernel<R, true>)
+  const bf16* heads_t; MegaTcGeo tg[TG_COUNT];
 };
 
 constexpr int kMegaStageBytes = 32 * 1024, kMegaAttnBytes = 40 * 1024;
+constexpr int kMegaTcImageBytes = 32 * 1024, kMegaTcPartBytes = 4 * 1024;   // tcgen05 consumer: activation image (32 k blocks x 1 KB), fp32 accumulator copy
 // consumer warps of the persistent kernel (+ 1 producer warp).  Nine warps leave 168 registers per thread (17 warps: 96,
 // with spills), and everything a warp does redundantly (norm statistics, index math, barrier and ring bookkeeping, the
 // per-stage reduction tree) is issued half as often: the warps share 4 issue slots.
@@ -1033,6 +1046,277 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
 #undef DBG
 }
 
+// ================================================================================================================
+// tcgen05 consumer of the persistent kernel (decode_step_kernel<R, true>).
+//
+// The FFMA2 consumer above needs ~0.55 us per 32 KB stage whatever feeds it; the tensor pipe drains a stage in a few
+// hundred cycles, so a phase is paced by HBM alone and what the ring prefetched while the previous phase exchanged its
+// activations is consumed at once.  "Swapped" operand roles: the activation rows are the UMMA A operand (M = 64), the
+// CTA's weight rows are the B operand (N = any multiple of 8 - so a matrix is cut by ROWS over all CTAs without a K
+// split across CTAs), the fp32 accumulator sits in tensor memory.
+//   all threads   poll the tagged activation words, normalise (PRO_NORM), write them as bf16 into the A image
+//                 [tile][S * R rows][64 k] (128-byte swizzle)
+//   warp 1        waits for ring stages and issues the MMAs; tcgen05.commit releases stages and signals the end
+//   all warps     read their TMEM quarter (tcgen05.ld) into the fp32 `part` buffer, then every thread runs one epilogue item
+// ================================================================================================================
+__device__ __forceinline__ void mega_produce_tc(const bf16* Wt, const MegaTcGeo& g, int K, unsigned char* ring, uint64_t* full_bar, uint64_t* empty_bar,
+                                                int S, int& gst, uint64_t pol, int lane) {
+  if ((int)blockIdx.x >= g.nunits) return;                    // this CTA has no unit of the matrix (consumers skip it alike)
+  const int nkb = K / (64 * g.S), nstage = (nkb + g.kps - 1) / g.kps;      // tiles of [S * RB rows][64 k]
+  const size_t tile = (size_t)g.S * g.RB * 128;
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(Wt) + (size_t)blockIdx.x * nkb * tile;
+  for (int st = 0; st < nstage; ++st, ++gst) {
+    const int slot = gst % S;
+    if (gst >= S) mbar_wait(&empty_bar[slot], ((gst / S) - 1) & 1);
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(min(g.kps, nkb - st * g.kps) * tile);
+      mbar_expect_tx(&full_bar[slot], bytes);
+      unsigned char* dst = ring + (size_t)slot * kMegaStageBytes;
+      const unsigned char* src = base + (size_t)st * g.kps * tile;
+      if (pol) bulk_g2s(dst, src, bytes, &full_bar[slot], pol);
+      else bulk_g2s_nohint(dst, src, bytes, &full_bar[slot]);
+    }
+    __syncwarp();
+  }
+}
+
+struct MegaTcState { uint64_t *acc_bar, *afree_bar; int nacc, nafree; uint32_t tmem; unsigned char* abuf; };
+
+template <int R, int NR, int PRO, int EPI>
+__device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcGeo& g, unsigned char* ring, float* part, uint64_t* full_bar,
+                                                uint64_t* empty_bar, MegaTcState& ts, float (*red)[kMW][4], int S, int& gst, bool release, int warp,
+                                                int lane, const uint32_t* xt, uint32_t tag_in, uint32_t* yt, uint32_t tag_out, const uint32_t* rt,
+                                                uint32_t tag_resid, uint32_t* qt, uint32_t* kvt, unsigned long long* stamp, int norm_pending,
+                                                const MegaQkvPre* qkv_pre) {
+  const int tid = threadIdx.x;                                // consumer threads 0 .. 255
+  if ((int)blockIdx.x >= g.nunits) return;                    // no unit of this matrix (the producer skipped it alike)
+  const int K = a.K, nchunk8 = K / 8, nkb = K / 64;
+  // activations: thread t holds elements [8 q, 8 q + 8) of every row for q = t + 256 c; spin on the operand loads
+  // themselves until every word carries the producing phase's tag
+  float xf[R][NR * 8];
+  for (unsigned spins = 0;; ++spins) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int c = 0; c < NR; ++c) {
+        const int q = tid + 256 * c;
+        if (q < nchunk8) {
+          const uint32_t* src = xt + (size_t)i * a.ldx + (size_t)q * 8;
+          const uint4 v0 = ld_relaxed_v4(src), v1 = ld_relaxed_v4(src + 4);
+          ok = ok && tags_ok(v0, tag_in) && tags_ok(v1, tag_in);
+          xf[i][c * 8 + 0] = untag(v0.x); xf[i][c * 8 + 1] = untag(v0.y); xf[i][c * 8 + 2] = untag(v0.z); xf[i][c * 8 + 3] = untag(v0.w);
+          xf[i][c * 8 + 4] = untag(v1.x); xf[i][c * 8 + 5] = untag(v1.y); xf[i][c * 8 + 6] = untag(v1.z); xf[i][c * 8 + 7] = untag(v1.w);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xf[i][c * 8 + e] = 0.f;
+        }
+      }
+    if (ok) break;
+    if (spins > kMegaSpinLimit) asm volatile("trap;");
+  }
+  if (stamp && tid == 0) *stamp = gtime();
+  if (PRO == PRO_NORM) {
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float sacc = 0.f, qacc = 0.f;
+#pragma unroll
+      for (int e = 0; e < NR * 8; ++e) { sacc += xf[i][e]; qacc = fmaf(xf[i][e], xf[i][e], qacc); }
+      sacc = warp_sum(sacc);
+      qacc = warp_sum(qacc);
+      if (lane == 0) { red[0][warp][i] = sacc; red[1][warp][i] = qacc; }
+    }
+    // norm parameters were copied to shared memory a layer ahead (see mega_consume)
+    if (norm_pending == 0) asm volatile("cp.async.wait_group 0;" ::: "memory"); else asm volatile("cp.async.wait_group 1;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
+    const float inv_k = 1.0f / (float)K;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const float tot = warp_sum(lane < kMW ? red[0][lane][i] : 0.f);     // same shuffle tree, same bits in every warp
+      const float tsq = warp_sum(lane < kMW ? red[1][lane][i] : 0.f);
+      const float mu = tot * inv_k;
+      mean[i] = (a.norm_kind == ZB_NORM_LAYERNORM) ? mu : 0.f;
+      const float var = (a.norm_kind == ZB_NORM_LAYERNORM) ? fmaxf(tsq * inv_k - mu * mu, 0.f) : tsq * inv_k;
+      rstd[i] = rsqrtf(var + a.eps);
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
+      const int q = tid + 256 * c;
+      if (q < nchunk8) {
+        const uint4 nwv = *reinterpret_cast<const uint4*>(a.nw + (size_t)q * 8);
+        const uint4 nbv = a.nb ? *reinterpret_cast<const uint4*>(a.nb + (size_t)q * 8) : make_uint4(0, 0, 0, 0);
+        const uint32_t gv[4] = {nwv.x, nwv.y, nwv.z, nwv.w}, bv[4] = {nbv.x, nbv.y, nbv.z, nbv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float g0 = bf16lo(gv[j]), g1 = bf16hi(gv[j]), b0 = bf16lo(bv[j]), b1 = bf16hi(bv[j]);
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            xf[i][c * 8 + 2 * j] = rbf((xf[i][c * 8 + 2 * j] - mean[i]) * rstd[i] * g0 + b0);
+            xf[i][c * 8 + 2 * j + 1] = rbf((xf[i][c * 8 + 2 * j + 1] - mean[i]) * rstd[i] * g1 + b1);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- this thread's epilogue item and its operands (residual value, RoPE cos/sin, KV page): fetched NOW so their L2
+  // round trips overlap the weight streaming instead of trailing it ----
+  const bool cfg = (EPI == EPI_HEADS && a.cfg_scale != 1.0f);
+  const int rows_out = cfg ? a.B : R;
+  const int nu = (EPI == EPI_QKV) ? g.RB / 2 : (EPI == EPI_SILU) ? g.RBv : g.RB;
+  const int ej = tid / rows_out, ei = tid % rows_out;
+  int en0, en1, lr0, lr1;
+  if (EPI == EPI_QKV) { lr0 = 2 * ej; lr1 = lr0 + 1; en0 = (int)blockIdx.x * g.RB + lr0; en1 = en0 + 1; }
+  else if (EPI == EPI_SILU) { lr0 = ej; lr1 = g.RBv + ej; en0 = (int)blockIdx.x * g.RBv + ej; en1 = en0 + a.F; }
+  else { lr0 = lr1 = ej; en0 = en1 = (int)blockIdx.x * g.RB + ej; }
+  const bool e_on = tid < nu * rows_out && en0 < (EPI == EPI_SILU ? a.F : a.N);
+  float pre_resid = 0.f;
+  float2 pre_cs = make_float2(1.f, 0.f);
+  int pre_pos = 0, pre_page = 0;
+  if (e_on) {
+    if (EPI == EPI_RESID) {                                   // written by an earlier phase; its tag is checked (one word, normally there already)
+      uint32_t w = ld_relaxed_u32(rt + (size_t)ei * a.ldr + en0);
+      for (unsigned spins = 0; (w & 0xffffu) != tag_resid; ++spins) {
+        if (spins > kMegaSpinLimit) asm volatile("trap;");
+        w = ld_relaxed_u32(rt + (size_t)ei * a.ldr + en0);
+      }
+      pre_resid = untag(w);
+    }
+    if (EPI == EPI_QKV && qkv_pre && qkv_pre->valid) { pre_pos = qkv_pre->pos; pre_page = qkv_pre->page; pre_cs = qkv_pre->cs; }
+  }
+
+  // ---- A image + MMAs ----
+  // Segment-diagonal GEMV: K is cut into S segments of Ks elements.  A row (s, i) = segment s of activation row i, B row
+  // (s', r) = segment s' of weight row r, so D[(s, i)][(s', r)] is the partial dot product over segment s for s == s' (the
+  // other blocks are never read) and y[i][r] = sum_s D[(s, i)][(s, r)].  One MMA then covers S * RB weight rows x 16 k
+  // (up to 8 KB) instead of RB x 16 (512 B): the tensor pipe needs ~(M + N) * 32 B / 128 cycles per MMA whatever is in the
+  // rows (measured, scripts/probes/mma_rate_probe.cu), far too slow for 16-row slices with nothing but real data in B.
+  const int SG = g.S, Ks = K / SG, nt = Ks / 64;               // tiles ("k' blocks") of the unit
+  const int rowsA = R * SG;                                    // <= 64
+  const uint32_t TA = (uint32_t)((rowsA + 7) / 8) * 1024u;     // image bytes per tile (the rows above read whatever follows)
+  const int TPC = min(nt, (int)(kMegaTcImageBytes / TA));      // tiles per image
+  const int gst0 = gst;
+  gst += (nt + g.kps - 1) / g.kps;
+  const uint32_t a_base = smem_u32(ts.abuf);
+  const uint32_t idesc = make_idesc(64, SG * g.RB);
+  const uint32_t tile = (uint32_t)(SG * g.RB) * 128u;
+  int slot = gst0 % S, w = 0;                                  // ring position of tile t (warp-uniform, advanced by every thread alike)
+  uint32_t par = (uint32_t)((gst0 / S) & 1);
+  for (int t0 = 0; t0 < nt; t0 += TPC) {
+    if (t0 > 0) {                                              // the MMAs of the previous image have read it
+      mbar_wait(ts.afree_bar, (uint32_t)(ts.nafree & 1));
+      ++ts.nafree;
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
+      const int q = tid + 256 * c;
+      if (q < nchunk8) {
+        const int k0 = q * 8, sg = k0 / Ks, kk = k0 - sg * Ks, t = kk >> 6, j = (kk & 63) >> 3;
+        if (t >= t0 && t < t0 + TPC) {
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            const int l = sg * R + i;
+            const uint32_t dst = a_base + (uint32_t)(t - t0) * TA + (uint32_t)(l >> 3) * 1024u + (uint32_t)(l & 7) * 128u + (uint32_t)((j ^ (l & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16(xf[i][c * 8 + 0], xf[i][c * 8 + 1])),
+                         "r"(pack_bf16(xf[i][c * 8 + 2], xf[i][c * 8 + 3])), "r"(pack_bf16(xf[i][c * 8 + 4], xf[i][c * 8 + 5])),
+                         "r"(pack_bf16(xf[i][c * 8 + 6], xf[i][c * 8 + 7]))
+                         : "memory");
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
+    const int t1 = min(nt, t0 + TPC);
+    if (warp_id_uniform() == 1) {                             // the whole warp walks the ring on uniform values, one elected lane issues (tc.cuh: elect_one)
+      tc_fence_after();
+      uint32_t a_tile = a_base;
+      for (int t = t0; t < t1; ++t, a_tile += TA) {
+        if (w == 0 || t == t0) { mbar_wait(&full_bar[slot], par); tc_fence_after(); }
+        const uint64_t da = make_smem_desc(a_tile);
+        const uint64_t db = make_smem_desc(smem_u32(ring) + (uint32_t)slot * kMegaStageBytes + (uint32_t)w * tile);
+        const bool last_of_stage = (w == g.kps - 1 || t == nt - 1);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma(ts.tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (t | kk) != 0 ? 1u : 0u);
+          if (release && last_of_stage) tc_commit(&empty_bar[slot]);
+        }
+        __syncwarp();
+        if (last_of_stage) { w = 0; if (++slot == S) { slot = 0; par ^= 1u; } } else ++w;
+      }
+      if (elect_one()) tc_commit(t1 == nt ? ts.acc_bar : ts.afree_bar);
+      __syncwarp();
+    }
+  }
+  // ---- accumulator -> part[(local weight row * S + segment) * R + activation row] ----
+  // accumulator row l = s * R + i sits in TMEM lane (l / 16) * 32 + l % 16 (M = 64: 16 rows per 32-lane quarter, measured with
+  // scripts/probes/tmem_layout_probe.cu); warps q and q + 4 may touch quarter q and split its column tiles
+  {
+    const int qd = warp & 3, half = warp >> 2;
+    if (16 * qd < rowsA) {
+      mbar_wait(ts.acc_bar, (uint32_t)(ts.nacc & 1));
+      tc_fence_after();
+      const int l = 16 * qd + (lane & 15), my_s = l / R, my_i = l - my_s * R;
+      const bool mine = lane < 16 && l < rowsA;
+      const int s_lo = (16 * qd) / R, s_hi = min(SG, (16 * qd + 16) / R);
+      int cnt = 0;
+      for (int sg = s_lo; sg < s_hi; ++sg)
+        for (int c8 = 0; c8 < g.RB / 8; ++c8, ++cnt) {
+          if ((cnt & 1) != half) continue;
+          float v[8];
+          tc_ld8(ts.tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(sg * g.RB + c8 * 8), v);
+          if (mine && sg == my_s) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[((c8 * 8 + j) * SG + sg) * R + my_i] = v[j];
+          }
+        }
+      tc_fence_before();
+    }
+  }
+  ++ts.nacc;
+  asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
+
+  if (e_on) {
+    float v0 = 0.f, v1 = 0.f;                                  // segment partials summed in segment order
+    for (int sg = 0; sg < SG; ++sg) { v0 += part[(lr0 * SG + sg) * R + ei]; v1 += part[(lr1 * SG + sg) * R + ei]; }
+    if (EPI == EPI_RESID) {
+      st_relaxed_u32(yt + (size_t)ei * a.ldy + en0, tag_word(pre_resid + rbf(v0), tag_out));
+    } else if (EPI == EPI_STORE) {
+      st_relaxed_u32(yt + (size_t)ei * a.ldy + en0, tag_word(v0, tag_out));
+    } else if (EPI == EPI_SILU) {                            // same ops as gemv_epilogue<EPI_SILU>
+      const float yv = rbf(v0), gt = rbf(v1);
+      const float sg = rbf(gt / (1.0f + expf(-gt)));
+      st_relaxed_u32(yt + (size_t)ei * a.ldy + en0, tag_word(__fmul_rn(yv, sg), tag_out));
+    } else if (EPI == EPI_QKV) {
+      const int qn_ = a.Hq * a.hd, kn_ = a.Hkv * a.hd;
+      float o0 = rbf(v0), o1 = rbf(v1);
+      if (en0 < qn_ + kn_) {                                 // same un-contracted fp32 ops as gemv_epilogue / _torch.py:57-68
+        const float r0 = __fsub_rn(__fmul_rn(o0, pre_cs.x), __fmul_rn(o1, pre_cs.y));
+        const float r1 = __fadd_rn(__fmul_rn(o1, pre_cs.x), __fmul_rn(o0, pre_cs.y));
+        o0 = r0; o1 = r1;
+      }
+      if (en0 < qn_) {
+        st_relaxed_u32(qt + (size_t)ei * qn_ + en0, tag_word(o0, tag_out));
+        st_relaxed_u32(qt + (size_t)ei * qn_ + en1, tag_word(o1, tag_out));
+      } else {
+        const int kvsel = en0 < qn_ + kn_ ? 0 : 1;
+        const int c0i = en0 - qn_ - kvsel * kn_, c1i = en1 - qn_ - kvsel * kn_;
+        st_relaxed_u32(kvt + ((size_t)ei * 2 + kvsel) * kn_ + c0i, tag_word(o0, tag_out));
+        st_relaxed_u32(kvt + ((size_t)ei * 2 + kvsel) * kn_ + c1i, tag_word(o1, tag_out));
+        bf16* pb = a.kv_layer + ((size_t)pre_page * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
+        const int tk = pre_pos % ZB_PAGE_TOKENS;
+        pb[((size_t)(c0i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c0i % a.hd)] = f2bf(o0);
+        pb[((size_t)(c1i / a.hd) * ZB_PAGE_TOKENS + tk) * a.hd + (c1i % a.hd)] = f2bf(o1);
+      }
+    } else {
+      float u0 = 0.f;
+      if (cfg) for (int sg = 0; sg < SG; ++sg) u0 += part[(lr0 * SG + sg) * R + a.B + ei];
+      gemv_epilogue<EPI>(a, ei, en0, en1, false, v0, 0.f, u0, 0.f);
+    }
+  }
+}
+
 // K/V of the tokens cached by EARLIER steps for this CTA's first attention unit of the layer: issued before the
 // in_proj phase so the tile is already in shared memory when the attention phase starts
 struct MegaAttnMeta { int n_old, page, g, kv_len; };          // step constants of this CTA's first attention unit
@@ -1188,23 +1472,35 @@ __device__ __forceinline__ void mega_fill(GemvArgs& a, const MegaArgs& m, int R)
   a.page_table = m.page_table; a.max_pages = m.max_pages; a.F = m.F; a.B = m.B; a.cfg_scale = m.cfg_scale; a.logits = m.logits; a.QV = m.QV;
 }
 
-template <int R>
+template <int R, bool TC>
 __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __grid_constant__ MegaArgs m) {
   extern __shared__ __align__(128) unsigned char smem_m[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tc_bar[2];
   __shared__ float red[2][kMW][4];
+  __shared__ uint32_t tmem_slot;
   if (loop_idle(m.loop, m.T_delayed)) return;                 // same answer in every CTA: the loop state only changes in the sampler
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = m.ring_stages;
-  unsigned char* ring = smem_m;
-  float* part = reinterpret_cast<float*>(smem_m + (size_t)S * kMegaStageBytes);
-  unsigned char* attn_scratch = smem_m + (size_t)S * kMegaStageBytes + m.part_bytes;
+  // TC: the ring holds UMMA tiles (1024-byte aligned swizzle atoms), followed by the 32 KB activation image
+  unsigned char* ring = TC ? reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_m) + 1023) & ~(uintptr_t)1023) : smem_m;
+  unsigned char* abuf = ring + (size_t)S * kMegaStageBytes;
+  float* part = reinterpret_cast<float*>(abuf + (TC ? kMegaTcImageBytes : 0));
+  unsigned char* attn_scratch = reinterpret_cast<unsigned char*>(part) + m.part_bytes;
   bf16* nbuf = reinterpret_cast<bf16*>(attn_scratch + kMegaAttnBytes);   // [2 buffers][weight | bias][D]: norm parameters, copied a layer ahead
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kMW); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TC ? 1 : kMW); }
+    mbar_init(&tc_bar[0], 1); mbar_init(&tc_bar[1], 1);
     mbar_fence_init();
   }
+  if (TC && warp == 0) {                                      // 256 accumulator columns (N <= 256 weight rows per CTA and matrix)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tc_fence_before();
+  }
   __syncthreads();
+  MegaTcState ts;
+  ts.acc_bar = &tc_bar[0]; ts.afree_bar = &tc_bar[1]; ts.nacc = 0; ts.nafree = 0; ts.tmem = 0; ts.abuf = abuf;
+  if (TC) { tc_fence_after(); ts.tmem = tmem_slot; }
   const int qn = m.Hq * m.hd, nqkv = (m.Hq + 2 * m.Hkv) * m.hd;
   GemvArgs a;
 
@@ -1215,6 +1511,13 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     MegaLayer L = m.layers[0], Lnext = L;
     for (int li = 0; li < m.n_layer; ++li, L = Lnext) {
       if (li + 1 < m.n_layer) Lnext = m.layers[li + 1];       // the next layer's pointers are on their way while this one streams
+      if (TC) {
+        mega_produce_tc(L.in_t, m.tg[TG_QKV], m.D, ring, full_bar, empty_bar, S, gst, pol, lane);
+        mega_produce_tc(L.out_t, m.tg[TG_OUT], qn, ring, full_bar, empty_bar, S, gst, pol, lane);
+        mega_produce_tc(L.fc1_t, m.tg[TG_FC1], m.D, ring, full_bar, empty_bar, S, gst, pol, lane);
+        mega_produce_tc(L.fc2_t, m.tg[TG_FC2], m.F, ring, full_bar, empty_bar, S, gst, pol, lane);
+        continue;
+      }
       mega_fill(a, m, R);
       a.W = L.in_proj; a.N = nqkv; a.K = m.D;
       mega_produce<EPI_QKV>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
@@ -1224,6 +1527,10 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       mega_produce<EPI_SILU>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
       a.W = L.fc2; a.N = m.D; a.K = m.F;
       mega_produce<EPI_RESID>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+    }
+    if (TC) {
+      mega_produce_tc(m.heads_t, m.tg[TG_HEADS], m.D, ring, full_bar, empty_bar, S, gst, pol, lane);
+      return;
     }
     mega_fill(a, m, R);
     a.W = m.heads; a.N = m.QV; a.K = m.D;
@@ -1239,6 +1546,9 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
   const bool stamping = m.timeline && blockIdx.x == 0;
   // norm parameters -> shared memory: one 16-byte cp.async per consumer thread and buffer half
   auto norm_prefetch = [&](int buf, const bf16* w, const bf16* b) {
+    // TC: a CTA without a unit of the in_proj / fc1 matrix skips the phase that waits for this buffer, and two cp.async
+    // to one address in flight at once may land in either order.  Free for the others: nothing is pending here.
+    if (TC) asm volatile("cp.async.wait_group 0;" ::: "memory");
     const int chunks = m.D / 8;
     bf16* dstw = nbuf + (size_t)buf * 2 * m.D;
     for (int q = threadIdx.x; q < 2 * chunks; q += kMW * 32) {
@@ -1255,11 +1565,12 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     a.N = nqkv; a.K = m.D;
     int u_begin, nrows;
     mega_slice<EPI_QKV>(a, u_begin, nrows);
+    if (TC) { nrows = (int)blockIdx.x < m.tg[TG_QKV].nunits ? m.tg[TG_QKV].RB : 0; u_begin = (int)blockIdx.x * (m.tg[TG_QKV].RB / 2); }
     const int et = threadIdx.x;
     if (et < (nrows / 2) * R) {
       const int ej = et / R, ei = et % R;
       int en0, en1;
-      unit_rows<EPI_QKV>(a, u_begin + ej, en0, en1);
+      unit_rows<EPI_QKV>(a, u_begin + ej, en0, en1);            // (TC: interleaved pairs only, en0 = 2 * unit)
       qkv_pre.pos = m.lengths[ei];
       if (en0 < qn + m.Hkv * m.hd) {
         const int ri = m.rope_interleaved ? (en0 % m.hd) / 2 : (en0 % m.hd);
@@ -1302,9 +1613,14 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     mega_attention_prefetch(m, L.kv_layer, ameta, attn_scratch);
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
+      if (TC)
+        mega_consume_tc<R, 1, PRO_NORM, EPI_QKV>(a, m.tg[TG_QKV], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
+                                                 nullptr, TAG(ph), nullptr, 0u, m.qt, m.kvt, slot, 1, &qkv_pre);
+      else
       mega_consume<R, 2, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
                                                nullptr, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
     }
+    const int ph_in = ph;                                      // x was last written by phase ph_in - 1 (embedding or the previous fc2)
     MEGA_STAMP(); ++ph;
     // B: attention over the paged cache
     {
@@ -1327,10 +1643,18 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
         int g2 = gst0;
         unsigned long long* slot = MEGA_STAMP_SLOT();
         if (last) {
+          if (TC)
+            mega_consume_tc<R, 1, PRO_NONE, EPI_RESID>(a, m.tg[TG_OUT], ring, part, full_bar, empty_bar, ts, red, S, g2, true, warp, lane, src,
+                                                       TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph_in - 1), nullptr, nullptr, slot, 0, nullptr);
+          else
           mega_consume<R, 2, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane, src, TAG(ph - 1), m.xt, TAG(ph),
                                                      m.xt, nullptr, nullptr, slot);
         } else {
           uint32_t* dst = (src == m.y1t) ? m.ayt : m.y1t;
+          if (TC)
+            mega_consume_tc<R, 1, PRO_NONE, EPI_STORE>(a, m.tg[TG_OUT], ring, part, full_bar, empty_bar, ts, red, S, g2, false, warp, lane, src,
+                                                       TAG(ph - 1), dst, TAG(ph), nullptr, 0u, nullptr, nullptr, slot, 0, nullptr);
+          else
           mega_consume<R, 2, 4, PRO_NONE, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, g2, false, warp, lane, src, TAG(ph - 1), dst, TAG(ph),
                                                      nullptr, nullptr, nullptr, slot);
           src = dst;
@@ -1344,6 +1668,10 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     a.W = L.fc1; a.N = 2 * m.F; a.K = m.D; a.ldx = m.D; a.nw = nbuf + 2 * m.D; a.nb = L.norm2_b ? nbuf + 3 * m.D : nullptr; a.ldy = m.F;
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
+      if (TC)
+        mega_consume_tc<R, 1, PRO_NORM, EPI_SILU>(a, m.tg[TG_FC1], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
+                                                  m.ht, TAG(ph), nullptr, 0u, nullptr, nullptr, slot, 0, nullptr);
+      else
       mega_consume<R, 2, 4, PRO_NORM, EPI_SILU>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
                                                 nullptr, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 220 : nullptr);
     }
@@ -1354,7 +1682,15 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     a.W = L.fc2; a.N = m.D; a.K = m.F; a.ldx = m.F; a.ldy = m.D; a.ldr = m.D;
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
-      if (m.F == 8192)
+      if (TC) {
+        // x was last written by the out_proj pass two phases back (phase ph - 2)
+        if (m.F > 2048)
+          mega_consume_tc<R, 4, PRO_NONE, EPI_RESID>(a, m.tg[TG_FC2], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.ht,
+                                                     TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph - 2), nullptr, nullptr, slot, 0, nullptr);
+        else
+          mega_consume_tc<R, 1, PRO_NONE, EPI_RESID>(a, m.tg[TG_FC2], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.ht,
+                                                     TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph - 2), nullptr, nullptr, slot, 0, nullptr);
+      } else if (m.F == 8192)
         mega_consume<R, 4, 2, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
                                                    m.xt, nullptr, nullptr, slot);
       else
@@ -1368,10 +1704,21 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
   a.W = m.heads; a.N = m.QV; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = m.normf_b ? nbuf + m.D : nullptr;
   {
     unsigned long long* slot = MEGA_STAMP_SLOT();
+    if (TC)
+      mega_consume_tc<R, 1, PRO_NORM, EPI_HEADS>(a, m.tg[TG_HEADS], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
+                                                 nullptr, 0u, nullptr, 0u, nullptr, nullptr, slot, 0, nullptr);
+    else
     mega_consume<R, 2, 4, PRO_NORM, EPI_HEADS>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, 0u,
                                                nullptr, nullptr, nullptr, slot);
   }
   MEGA_STAMP();
+  if (TC) {                                                   // every accumulator read is behind the last phase's CTA barrier
+    asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
+    if (warp == 0) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ts.tmem), "r"(256u) : "memory");
+    }
+  }
   // CTA 0 can only get here after it consumed outputs of every CTA, i.e. after every CTA read the epoch
   if (blockIdx.x == 0 && threadIdx.x == 0) m.sync[1] = epoch + 1;
   if (m.steplog && blockIdx.x == 0 && threadIdx.x == 0 && m.loop) m.steplog[2 * min(m.loop->steps, 4000) + 1] = gtime();
@@ -1532,6 +1879,61 @@ __global__ void __launch_bounds__(256) gated_norm_kernel(GNormArgs a) {
 }
 
 // ------------------------------------------------------------------ host side ----------------
+// ---- tile-ordered weight copy for the tcgen05 consumer of the persistent kernel (MegaTcGeo) -------------------------
+struct PretileArgs { const bf16* W; uint4* out; int N, K, RB, RBv, F, nunits, S; };
+// one thread per 16-byte chunk of the output; physical chunk c of tile row n holds logical chunk c ^ (n % 8) (128-byte swizzle)
+__global__ void __launch_bounds__(256) pretile_kernel(PretileArgs a) {
+  const int NB = a.S * a.RB, Ks = a.K / a.S;                 // tile rows, k per segment
+  const size_t nt = (size_t)Ks / 64, total = (size_t)a.nunits * nt * NB * 8;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % 8), n = (int)((idx / 8) % NB);
+    const size_t t = (idx / (8 * (size_t)NB)) % nt, u = idx / (8 * (size_t)NB * nt);
+    const int sg = n / a.RB, r = n % a.RB;
+    const size_t kb = ((size_t)sg * Ks) / 64 + t;
+    long long row; bool valid;
+    if (a.RBv) {                                              // fc1: value rows, then the gate rows of the same features
+      const long long f = (long long)u * a.RBv + (r % a.RBv);
+      valid = f < a.F; row = (r < a.RBv ? 0 : a.F) + f;
+    } else {
+      row = (long long)u * a.RB + r; valid = row < a.N;
+    }
+    const int j = c ^ (n & 7);
+    a.out[idx] = valid ? __ldg(reinterpret_cast<const uint4*>(a.W + (size_t)row * a.K + kb * 64 + (size_t)j * 8)) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+inline int env_int(const char* name, int dflt);
+struct MegaTcPlan { MegaTcGeo g[TG_COUNT]; int K[TG_COUNT]; size_t off[TG_COUNT], layer_bytes, total; };
+bool mega_tc_plan(const zb_model_desc& d, int grid, int R, MegaTcPlan* p) {
+  memset(p, 0, sizeof(*p));
+  const int qn = d.n_heads * d.head_dim, nqkv = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim, QV = d.n_codebooks * d.head_vocab;
+  auto unit = [&](int N) { return ((N + grid - 1) / grid + 7) / 8 * 8; };
+  auto geo = [&](int kind, int N, int K, bool gated) -> bool {
+    MegaTcGeo& g = p->g[kind];
+    if (gated) { g.RBv = unit(N / 2); g.RB = 2 * g.RBv; g.nunits = (N / 2 + g.RBv - 1) / g.RBv; }
+    else { g.RBv = 0; g.RB = unit(N); g.nunits = (N + g.RB - 1) / g.RB; }
+    p->K[kind] = K;
+    if (K % 64 || K > 8192 || g.RB > 256 || g.nunits > grid) return false;
+    // segments: as many as fit the MMA (S * RB <= 256 columns, 4 rows x S <= 64 accumulator rows) and divide K into 64-k tiles
+    g.S = 1;
+    const int smax = env_int("ZB_MEGA_TC_SMAX", 16);          // (debug: 1 = plain row slices)
+    while (g.S < 16 && 2 * g.S <= smax && 2 * g.S * g.RB <= 256 && K % (2 * g.S * 64) == 0) g.S *= 2;
+    g.kps = kMegaStageBytes / (g.S * g.RB * 128);
+    const int items = (kind == TG_QKV ? g.RB / 2 : gated ? g.RBv : g.RB) * R;      // one epilogue item per consumer thread
+    return g.kps >= 1 && items <= kMW * 32;
+  };
+  if (!geo(TG_QKV, nqkv, d.d_model, false) || !geo(TG_OUT, d.d_model, qn, false) || !geo(TG_FC1, 2 * d.d_ff, d.d_model, true) ||
+      !geo(TG_FC2, d.d_model, d.d_ff, false) || !geo(TG_HEADS, QV, d.d_model, false))
+    return false;
+  if (d.d_model > 2048 || qn > 2048 || !d.rope_interleaved) return false;       // one 2048-k image per phase except fc2; pairs (2i, 2i+1)
+  size_t off = 0;
+  for (int k = 0; k < TG_HEADS; ++k) { p->off[k] = off; off += (size_t)p->g[k].nunits * p->g[k].RB * p->K[k] * 2; }
+  p->layer_bytes = off;
+  p->off[TG_HEADS] = (size_t)d.n_layer * off;
+  p->total = p->off[TG_HEADS] + (size_t)p->g[TG_HEADS].nunits * p->g[TG_HEADS].RB * p->K[TG_HEADS] * 2;
+  return true;
+}
+
 struct Scratch {
   bf16 *q, *attn_y, *y1, *h, *xn, *zx, *gn; float *part, *g; int32_t* counters; int nsplit;
 };
@@ -1890,8 +2292,54 @@ size_t zb_mega_arena_bytes(const zb_model* model, int R) {
   return ((size_t)R * (2 * d.d_model + 2 * qn + d.d_ff + 2 * kn)) * sizeof(uint32_t);
 }
 
-zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf) {
+bool zb_mega_tc_enabled(const zb_model* model, int R) {
+  const int enabled = env_int("ZB_MEGA_TC", 1);              // 0: FFMA2 consumer (read per session: tests compare both in one process)
+  MegaTcPlan p;
+  return enabled && mega_tc_plan(model->d, model->ctx->num_sms, R, &p);
+}
+
+// (re)build the tile-ordered weight copy: once per model, and after zb_model_weights_changed()
+static zb_status mega_tc_pretile(zb_ctx* ctx, const zb_model* model, const MegaTcPlan& p, cudaStream_t stream) {
   const zb_model_desc& d = model->d;
+  if (model->tcw && (model->tcw_bytes < p.total || model->tcw_grid != ctx->num_sms)) {
+    ZB_CUDA(ctx, cudaDeviceSynchronize());
+    ZB_CUDA(ctx, cudaFree(model->tcw));
+    model->tcw = nullptr; model->tcw_valid = false;
+  }
+  if (!model->tcw) {
+    ZB_CUDA(ctx, cudaMalloc(&model->tcw, p.total));
+    model->tcw_bytes = p.total; model->tcw_grid = ctx->num_sms; model->tcw_valid = false;
+  }
+  if (model->tcw_valid) return ZB_OK;
+  auto run = [&](const void* W, size_t off, int kind, int N, int F) -> zb_status {
+    PretileArgs a;
+    a.W = (const bf16*)W; a.out = (uint4*)((char*)model->tcw + off); a.N = N; a.K = p.K[kind]; a.RB = p.g[kind].RB; a.RBv = p.g[kind].RBv; a.F = F;
+    a.nunits = p.g[kind].nunits; a.S = p.g[kind].S;
+    pretile_kernel<<<ctx->num_sms * 8, 256, 0, stream>>>(a);
+    ZB_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return ZB_OK;
+  };
+  const int qn = d.n_heads * d.head_dim, nqkv = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim;
+  for (int li = 0; li < d.n_layer; ++li) {
+    const zb_layer& L = model->layers[li];
+    const size_t base = (size_t)li * p.layer_bytes;
+    if (zb_status st = run(L.in_proj, base + p.off[TG_QKV], TG_QKV, nqkv, 0)) return st;
+    if (zb_status st = run(L.out_proj, base + p.off[TG_OUT], TG_OUT, d.d_model, 0)) return st;
+    if (zb_status st = run(L.fc1, base + p.off[TG_FC1], TG_FC1, 2 * d.d_ff, d.d_ff)) return st;
+    if (zb_status st = run(L.fc2, base + p.off[TG_FC2], TG_FC2, d.d_model, 0)) return st;
+  }
+  if (zb_status st = run(d.heads, p.off[TG_HEADS], TG_HEADS, d.n_codebooks * d.head_vocab, 0)) return st;
+  model->tcw_valid = true;
+  (void)qn;
+  return ZB_OK;
+}
+
+zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf, cudaStream_t stream) {
+  const zb_model_desc& d = model->d;
+  MegaTcPlan tp;
+  const bool tc = mega_tc_plan(d, ctx->num_sms, 2, &tp) && zb_mega_tc_enabled(model, 2) && d.heads;
+  if (tc) { if (zb_status st = mega_tc_pretile(ctx, model, tp, stream)) return st; }
   const size_t page_elems = (size_t)2 * d.n_heads_kv * ZB_PAGE_TOKENS * d.head_dim;
   MegaLayer* out = (MegaLayer*)host_buf;
   static const int share = env_int("ZB_DEBUG_SHARE_LAYERS", 0);   // debug: every layer streams layer 0's weights (L2-resident experiment)
@@ -1902,6 +2350,12 @@ zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cach
     out[li].out_proj = (const bf16*)L.out_proj; out[li].norm2_w = (const bf16*)L.norm2_w; out[li].norm2_b = (const bf16*)L.norm2_b;
     out[li].fc1 = (const bf16*)L.fc1; out[li].fc2 = (const bf16*)L.fc2;
     out[li].kv_layer = (bf16*)cache->kv_pages + (size_t)model->attn_index[li] * cache->num_pages * page_elems;
+    out[li].in_t = out[li].out_t = out[li].fc1_t = out[li].fc2_t = nullptr;
+    if (tc) {
+      const char* base = (const char*)model->tcw + (size_t)li * tp.layer_bytes;
+      out[li].in_t = (const bf16*)(base + tp.off[TG_QKV]); out[li].out_t = (const bf16*)(base + tp.off[TG_OUT]);
+      out[li].fc1_t = (const bf16*)(base + tp.off[TG_FC1]); out[li].fc2_t = (const bf16*)(base + tp.off[TG_FC2]);
+    }
   }
   return ZB_OK;
 }
@@ -1967,15 +2421,22 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     const int max_items = std::max(((d.d_ff + grid - 1) / grid) * R, ((m.QV + grid - 1) / grid) * R);
     ZB_REQUIRE(ctx, max_items <= kMW * 32 && ((d.d_model + grid - 1) / grid) * R <= kMW * 32, "persistent decode: %d epilogue items per CTA", max_items);
   }
+  MegaTcPlan tp;
+  const bool tc = zb_mega_tc_enabled(model, R) && mega_tc_plan(d, grid, R, &tp) && model->tcw && model->tcw_valid;
+  if (tc) {
+    for (int k = 0; k < TG_COUNT; ++k) m.tg[k] = tp.g[k];
+    m.heads_t = (const bf16*)((const char*)model->tcw + tp.off[TG_HEADS]);
+    pb = kMegaTcPartBytes;
+  }
   const size_t attn_bytes = kMegaAttnBytes + (size_t)4 * d.d_model * sizeof(bf16);   // attention tiles + two norm-parameter buffers
-  const size_t avail = 227 * 1024 - 2048;
+  const size_t avail = 227 * 1024 - 2048 - (tc ? kMegaTcImageBytes + 1024 : 0);      // (tc: activation image, 1024-byte alignment of the ring)
   int stages = (int)((avail - pb - attn_bytes) / kMegaStageBytes);
   if (stages > kMaxStages) stages = kMaxStages;
   ZB_REQUIRE(ctx, stages >= 3, "persistent decode: not enough shared memory for the ring");
   m.ring_stages = stages; m.part_bytes = (int)pb;
   static const int evict_first = env_int("ZB_MEGA_EVICT_FIRST", 1);
   m.evict_first = evict_first;
-  const size_t smem = (size_t)stages * kMegaStageBytes + pb + attn_bytes;
+  const size_t smem = (size_t)stages * kMegaStageBytes + pb + attn_bytes + (tc ? kMegaTcImageBytes + 1024 : 0);
   auto launch = [&](auto kernel) -> zb_status {
     ZB_CUDA(ctx, zb_ensure_smem(ctx, kernel, smem));
     cudaLaunchConfig_t cfg = {};
@@ -1988,8 +2449,11 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     ctx->launches++;
     return ZB_OK;
   };
-  if (R <= 2) return launch(decode_step_kernel<2>);
-  return launch(decode_step_kernel<4>);
+  if (env_int("ZB_MEGA_VERBOSE", 0) && loop && ctx->launches % 64 == 0)
+    fprintf(stderr, "[zb] persistent decode step: %s consumer, %d stages, smem %zu\n", tc ? "tcgen05" : "FFMA2", stages, smem);
+  if (tc) return R <= 2 ? launch(decode_step_kernel<2, true>) : launch(decode_step_kernel<4, true>);
+  if (R <= 2) return launch(decode_step_kernel<2, false>);
+  return launch(decode_step_kernel<4, false>);
 }
 
 // ---- diagnostics: launch ONE production kernel on scratch activations (bench.py roofline leg) ----

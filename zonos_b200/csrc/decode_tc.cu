@@ -287,26 +287,30 @@ __device__ __forceinline__ void tc_issue(const TcArgs& a, const TcGemm& g, unsig
   if (!u.active) return;
   const int S = a.stages, SB = a.bstages, n = u.kb1 - u.kb0;
   const uint32_t idesc = make_idesc(128, a.Rp);
-  uint32_t accumulate = 0;
+  const bool lane0 = (threadIdx.x & 31) == 0;
+  // the whole warp walks the rings on warp-uniform values, one elected lane issues (tc.cuh: elect_one)
   for (int j = 0; j < n; j += kKbSlot, ++gst, ++bst) {
     const int cnt = min(kKbSlot, n - j);
     const int slot = gst % S, bslot = bst % SB;
     mbar_wait(&bfull[bslot], (uint32_t)((bst / SB) & 1));
-    ring_wait_full(full_bar, slot_use, S, gst, true);
+    ring_wait_full(full_bar, slot_use, S, gst, lane0);
     tc_fence_after();
-    for (int e = 0; e < cnt; ++e) {
-      const uint64_t da = make_smem_desc(smem_u32(ring + (size_t)slot * kSlot + (size_t)e * (kSlot / kKbSlot)));
-      const uint64_t db = make_smem_desc(smem_u32(bring + (size_t)bslot * a.bslot_bytes + (size_t)e * a.Rp * 128));
+    const uint32_t ra = smem_u32(ring + (size_t)slot * kSlot), rb = smem_u32(bring + (size_t)bslot * a.bslot_bytes);
+    if (elect_one()) {
+      for (int e = 0; e < cnt; ++e) {
+        const uint64_t da = make_smem_desc(ra + (uint32_t)e * (kSlot / kKbSlot));
+        const uint64_t db = make_smem_desc(rb + (uint32_t)e * (uint32_t)a.Rp * 128u);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {                    // UMMA K = 16 bf16 = 32 bytes
-        tc_mma(tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accumulate);
-        accumulate = 1;
+        for (int kk = 0; kk < 4; ++kk)                    // UMMA K = 16 bf16 = 32 bytes
+          tc_mma(tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (j | e | kk) ? 1u : 0u);
       }
+      tc_commit(&empty_bar[slot]);
+      tc_commit(&bempty[bslot]);
     }
-    tc_commit(&empty_bar[slot]);
-    tc_commit(&bempty[bslot]);
+    __syncwarp();
   }
-  tc_commit(acc_full);
+  if (elect_one()) tc_commit(acc_full);
+  __syncwarp();
 }
 
 // ---- accumulator -> fp32 partials ws[k slice][activation row][feature] -----------------------------------------
@@ -839,9 +843,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       }
       tc_produce(a, a.g[G_HEADS], &acts->map[0], G_HEADS, ring, full_bar, empty_bar, gst);
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+  } else if (warp_id_uniform() == 1) {
+    // ===== MMA issuer (whole warp, see tc_issue) =====
+    {
       int gst = 0, bst = 0;
 #define TC_ISSUE(kind) tc_issue(a, a.g[kind], ring, bring, full_bar, empty_bar, bfull, bempty, &acc_full, slot_use, tmem, gst, bst)
       for (int li = 0; li < a.n_layer; ++li) {

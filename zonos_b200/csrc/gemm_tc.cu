@@ -90,23 +90,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         tma_load_2d(sb, &a.map_x, (kb0 + kb) * TC_BK, m0, &full_bar[s]);
       }
     }
-  } else if (warp == 5) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(TC_BM, BN);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % a.stages;
-        mbar_wait(&full_bar[s], (kb / a.stages) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
-        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+  } else if (warp_id_uniform() == 5) {
+    // ===== MMA issuer: the whole warp walks the ring on uniform values, one elected lane issues (see elect_one) =====
+    const uint32_t idesc = make_idesc(TC_BM, BN);
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % a.stages;
+      mbar_wait(&full_bar[s], (kb / a.stages) & 1);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(base + (size_t)s * stage_bytes);
+      const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+      if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < TC_BK / 16; ++kk)          // UMMA K = 16 bf16 = 32 bytes: advance the start address
+        for (int kk = 0; kk < 4; ++kk)                    // UMMA K = 16 bf16 = 32 bytes: advance the start address
           tc_mma(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
         tc_commit(&empty_bar[s]);                        // frees the smem slot when these MMAs retire
       }
-      tc_commit(&tmem_full_bar);                         // accumulator complete
+      __syncwarp();
     }
+    if (elect_one()) tc_commit(&tmem_full_bar);          // accumulator complete
+    __syncwarp();
   } else {
     // ===== epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32) = weight rows of the tile =====
     mbar_wait(&tmem_full_bar, 0);

@@ -27,6 +27,10 @@ struct zb_model {
   int n_attn = 0, n_mamba = 0;
   std::vector<int> attn_index;    // layer -> index among attention layers (or -1)
   std::vector<int> mamba_index;
+  // Weight copy in the tile order of the persistent kernel's tcgen05 consumer (decode.cu, MegaTcGeo): built by the first
+  // generate session that takes that path, rebuilt after zb_model_weights_changed(); owned by the model.
+  mutable void* tcw = nullptr; mutable size_t tcw_bytes = 0; mutable int tcw_grid = 0; mutable bool tcw_valid = false;
+  ~zb_model() { if (tcw) { cudaSetDevice(ctx->device); cudaFree(tcw); } }
 };
 
 struct zb_sample_launch {
@@ -68,7 +72,7 @@ bool zb_mega_supported(const zb_model* model, int R);
 unsigned long long* zb_debug_steplog_ptr();                  // debug (zb_debug_steplog), nullptr normally
 size_t zb_mega_layers_bytes(const zb_model* model);
 size_t zb_mega_arena_bytes(const zb_model* model, int R);     // tagged activation words of one generate session (zeroed by the caller)
-zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf);
+zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf, cudaStream_t stream);
 zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, const void* mega_layers_dev, unsigned* sync,
                                 uint32_t* arena, int R, int max_kv_len, float cfg_scale, float* logits, const int64_t* delayed, int T_delayed,
                                 const zb_loop_state* loop, cudaStream_t stream);

@@ -73,6 +73,18 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// One lane of a converged warp.  The MMA issuer runs as a WHOLE warp on warp-uniform values and issues under this
+// predicate: nvcc then keeps descriptors and addresses in uniform registers and emits back-to-back UTCHMMA.  With an
+// `if (lane == 0)` body it cannot prove uniformity and wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY loop:
+// measured 153 cycles per MMA against 39 (M = 128) / 23 (M = 64) for N = 16 (scripts/probes/mma_rate_probe.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -6,12 +6,6 @@
 #include <cstdlib>
 #include "tc.cuh"
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
 __global__ void __launch_bounds__(128, 1) probe(int M, int N, int count, int nacc, int distinct, long long* out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -32,8 +26,9 @@ __global__ void __launch_bounds__(128, 1) probe(int M, int N, int count, int nac
   if (distinct >= 4 && warp_u == 1) {
     // the whole warp runs the loop on uniform values; one elected lane issues (CUTLASS / DeepGEMM pattern)
     const uint32_t idesc = make_idesc(M, N);
-    const uint32_t a_base = smem_u32(smem), b_base = a_base + 64 * 1024;
+    const uint32_t a_base = smem_u32(smem), b_base = a_base + 32 * 1024;
     const uint32_t bstep = (uint32_t)N * 128u >> 4;
+    const int wrap = max(1, min(16, (128 * 1024) / (N * 128)));     // k blocks before the descriptors wrap
     for (int rep = 0; rep < 3; ++rep) {
       const long long t0 = clock64();
       uint64_t da = make_smem_desc(a_base), db = make_smem_desc(b_base);
@@ -46,7 +41,7 @@ __global__ void __launch_bounds__(128, 1) probe(int M, int N, int count, int nac
         }
         __syncwarp();
         da += 64; db += bstep;
-        if ((kb & 15) == 15) { da -= 64 * 16; db -= bstep * 16; }
+        if ((kb + 1) % wrap == 0) { da -= 64 * wrap; db -= bstep * wrap; }
       }
       const long long t1 = clock64();
       if (elect_one()) tc_commit(&bar);

@@ -144,6 +144,11 @@ def main():
                 tot += done - prev
                 prev = done
             print(f"   layer total {1e-3 * tot:.2f} us")
+            if tc:
+                for nme, off in (("in_proj", 200), ("out2", 208), ("fc1", 216), ("fc2", 224)):
+                    x = t[off:off + 6]
+                    lab = ["normalised", "image written + CTA barrier", "accumulator complete", "read back + CTA barrier", "epilogue done"]
+                    print(f"   layer 1 {nme:8s}: " + "  ".join(f"{l} +{1e-3 * float(v - x[0]):.2f}" for l, v in zip(lab, x[1:])))
     elif args.timeline:
         import ctypes as C
         lib = _lib.load()

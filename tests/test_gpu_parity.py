@@ -279,6 +279,16 @@ def test_generate_tcgen05_decode_step_matches_oracle(B, monkeypatch):
         assert sum(same) >= 0.5 * B, f"only {sum(same)} of {B} utterances kept the oracle's history"
 
 
+@pytest.mark.parametrize("case", ["tiny_b1", "tiny_b1_eos", "tiny_b2_prefix_eos", "tiny_b1_greedy"])
+def test_generate_mega_tcgen05_consumer_golden(case, monkeypatch):
+    """The persistent B <= 2 kernel with its tcgen05 consumer (decode.cu: mega_consume_tc, opt-in with ZB_MEGA_TC=1: tile-ordered
+    weight copy, segment-diagonal MMAs, accumulator read back from tensor memory) on the reference-recorded cases.  Run in
+    this order on purpose: a batch-2 session after batch-1 sessions once exposed a cp.async ordering race in CTAs that have
+    no unit of a matrix."""
+    monkeypatch.setenv("ZB_MEGA_TC", "1")
+    test_generate_matches_reference_golden(case)
+
+
 def test_generate_tcgen05_eos_and_prefix_golden(monkeypatch):
     """The reference-recorded B=2 case with an audio prefix, EOS and the unified sampler, through decode_tc.cu."""
     monkeypatch.setenv("ZB_DECODE_TC", "2")
@@ -500,6 +510,32 @@ def test_full_size_logits_match_oracle(full_model):
     ref = o_gen.generate(oracle, cond, None, N, 2.0, B, dict(min_p=0.1), q_stream=q, trace=otrace)
     check_generate_against_oracle(trace, otrace, dict(min_p=0.1), q, 0)
     assert codes.shape == ref.shape
+
+
+def test_mega_tcgen05_consumer_full_size_matches_ffma_consumer(full_model, monkeypatch):
+    """Full-size weights, batch 1 and 2: the two consumers of the persistent kernel must produce the same tokens over the first
+    steps (identical rounding points; only the fp32 summation order inside a dot product differs) and logits within LOGIT_ATOL
+    while the histories agree."""
+    model, _ = full_model
+    for B in (1, 2):
+        cond = make_conditioning(2 * B, 40, TRANSFORMER_DIMS["d_model"], seed=4)
+        q = q_stream_from_seed(5, 24 + 9, B)
+        out = {}
+        for tc in ("1", "0"):
+            monkeypatch.setenv("ZB_MEGA_TC", tc)
+            trace = {}
+            codes = model.generate(cond.to(DEV), max_new_tokens=24, batch_size=B, q_stream=q, trace=trace)
+            lg = trace["logits"]
+            out[tc] = (codes.cpu(), (torch.stack(list(lg)) if isinstance(lg, list) else lg).cpu(), trace["delayed"].cpu())
+        (c1, l1, d1), (c0, l0, d0) = out["1"], out["0"]
+        n = min(l1.shape[0], l0.shape[0], d1.shape[-1] - 1)
+        alive = torch.ones(B, dtype=torch.bool)
+        for call in range(n):
+            for b in range(B):
+                if alive[b]:
+                    assert logits_close(l1[call, b], l0[call, b]) <= 1.0, (B, call, b)
+            alive &= (d1[..., 1 + call] == d0[..., 1 + call]).all(dim=1)
+        assert int(alive.sum()) >= B - 1, "the consumers parted ways on more than one utterance within 24 steps"
 
 
 def test_full_size_batch64_matches_oracle_on_a_subset(full_model):

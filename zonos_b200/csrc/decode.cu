@@ -1087,7 +1087,8 @@ __device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcG
                                                 uint64_t* empty_bar, MegaTcState& ts, float (*red)[kMW][4], int S, int& gst, bool release, int warp,
                                                 int lane, const uint32_t* xt, uint32_t tag_in, uint32_t* yt, uint32_t tag_out, const uint32_t* rt,
                                                 uint32_t tag_resid, uint32_t* qt, uint32_t* kvt, unsigned long long* stamp, int norm_pending,
-                                                const MegaQkvPre* qkv_pre) {
+                                                const MegaQkvPre* qkv_pre, unsigned long long* dbg = nullptr) {
+#define DBG(i) do { if (dbg && threadIdx.x == 0) dbg[i] = gtime(); } while (0)
   const int tid = threadIdx.x;                                // consumer threads 0 .. 255
   if ((int)blockIdx.x >= g.nunits) return;                    // no unit of this matrix (the producer skipped it alike)
   const int K = a.K, nchunk8 = K / 8, nkb = K / 64;
@@ -1116,6 +1117,7 @@ __device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcG
     if (spins > kMegaSpinLimit) asm volatile("trap;");
   }
   if (stamp && tid == 0) *stamp = gtime();
+  DBG(0);
   if (PRO == PRO_NORM) {
     float mean[R], rstd[R];
 #pragma unroll
@@ -1186,15 +1188,21 @@ __device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcG
     if (EPI == EPI_QKV && qkv_pre && qkv_pre->valid) { pre_pos = qkv_pre->pos; pre_page = qkv_pre->page; pre_cs = qkv_pre->cs; }
   }
 
+  DBG(1);
   // ---- A image + MMAs ----
   // Segment-diagonal GEMV: K is cut into S segments of Ks elements.  A row (s, i) = segment s of activation row i, B row
   // (s', r) = segment s' of weight row r, so D[(s, i)][(s', r)] is the partial dot product over segment s for s == s' (the
   // other blocks are never read) and y[i][r] = sum_s D[(s, i)][(s, r)].  One MMA then covers S * RB weight rows x 16 k
   // (up to 8 KB) instead of RB x 16 (512 B): the tensor pipe needs ~(M + N) * 32 B / 128 cycles per MMA whatever is in the
   // rows (measured, scripts/probes/mma_rate_probe.cu), far too slow for 16-row slices with nothing but real data in B.
+  // Accumulator row (s, i) is placed in TMEM quarter s % NQ, slot (s / NQ) * R + i of its 16 rows (M = 64 keeps 16 rows per
+  // 32-lane quarter): every quarter then needs the columns of only S / NQ segments on the way back, on two warps each.
   const int SG = g.S, Ks = K / SG, nt = Ks / 64;               // tiles ("k' blocks") of the unit
-  const int rowsA = R * SG;                                    // <= 64
-  const uint32_t TA = (uint32_t)((rowsA + 7) / 8) * 1024u;     // image bytes per tile (the rows above read whatever follows)
+  const int NQ = min(4, SG), spq = (SG / NQ) * R;              // quarters in use, slots per quarter (<= 16)
+  const bool wide = spq > 8;
+  // image of one tile: quarter q = UMMA row groups 2q, 2q + 1.  With <= 8 slots only the even groups hold data: a stride
+  // of 512 bytes between groups puts them 1 KB apart (the odd groups overlap them and land in lanes nobody reads)
+  const uint32_t QS = wide ? 2048u : 1024u, TA = (uint32_t)NQ * QS, sbo = wide ? 1024u : 512u;
   const int TPC = min(nt, (int)(kMegaTcImageBytes / TA));      // tiles per image
   const int gst0 = gst;
   gst += (nt + g.kps - 1) / g.kps;
@@ -1216,8 +1224,9 @@ __device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcG
         if (t >= t0 && t < t0 + TPC) {
 #pragma unroll
           for (int i = 0; i < R; ++i) {
-            const int l = sg * R + i;
-            const uint32_t dst = a_base + (uint32_t)(t - t0) * TA + (uint32_t)(l >> 3) * 1024u + (uint32_t)(l & 7) * 128u + (uint32_t)((j ^ (l & 7)) << 4);
+            const int qd = sg & (NQ - 1), sl = (sg / NQ) * R + i;
+            const uint32_t dst = a_base + (uint32_t)(t - t0) * TA + (uint32_t)qd * QS + (uint32_t)(sl >> 3) * 1024u + (uint32_t)(sl & 7) * 128u +
+                                 (uint32_t)((j ^ (sl & 7)) << 4);
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16(xf[i][c * 8 + 0], xf[i][c * 8 + 1])),
                          "r"(pack_bf16(xf[i][c * 8 + 2], xf[i][c * 8 + 3])), "r"(pack_bf16(xf[i][c * 8 + 4], xf[i][c * 8 + 5])),
                          "r"(pack_bf16(xf[i][c * 8 + 6], xf[i][c * 8 + 7]))
@@ -1228,13 +1237,14 @@ __device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcG
     }
     fence_proxy_async_smem();
     asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
+    if (t0 == 0) DBG(2);
     const int t1 = min(nt, t0 + TPC);
     if (warp_id_uniform() == 1) {                             // the whole warp walks the ring on uniform values, one elected lane issues (tc.cuh: elect_one)
       tc_fence_after();
       uint32_t a_tile = a_base;
       for (int t = t0; t < t1; ++t, a_tile += TA) {
         if (w == 0 || t == t0) { mbar_wait(&full_bar[slot], par); tc_fence_after(); }
-        const uint64_t da = make_smem_desc(a_tile);
+        const uint64_t da = make_smem_desc_sbo(a_tile, sbo);
         const uint64_t db = make_smem_desc(smem_u32(ring) + (uint32_t)slot * kMegaStageBytes + (uint32_t)w * tile);
         const bool last_of_stage = (w == g.kps - 1 || t == nt - 1);
         if (elect_one()) {
@@ -1249,37 +1259,71 @@ __device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcG
       __syncwarp();
     }
   }
-  // ---- accumulator -> part[(local weight row * S + segment) * R + activation row] ----
-  // accumulator row l = s * R + i sits in TMEM lane (l / 16) * 32 + l % 16 (M = 64: 16 rows per 32-lane quarter, measured with
-  // scripts/probes/tmem_layout_probe.cu); warps q and q + 4 may touch quarter q and split its column tiles
+  // ---- accumulator -> part[(segment * R + activation row) * RB + local weight row] ----
+  // warps q and q + 4 may touch quarter q; they take its column pieces in turn.  A lane keeps the pieces of its own segment.
   {
     const int qd = warp & 3, half = warp >> 2;
-    if (16 * qd < rowsA) {
+    if (qd < NQ) {
       mbar_wait(ts.acc_bar, (uint32_t)(ts.nacc & 1));
       tc_fence_after();
-      const int l = 16 * qd + (lane & 15), my_s = l / R, my_i = l - my_s * R;
-      const bool mine = lane < 16 && l < rowsA;
-      const int s_lo = (16 * qd) / R, s_hi = min(SG, (16 * qd + 16) / R);
-      int cnt = 0;
-      for (int sg = s_lo; sg < s_hi; ++sg)
-        for (int c8 = 0; c8 < g.RB / 8; ++c8, ++cnt) {
-          if ((cnt & 1) != half) continue;
-          float v[8];
-          tc_ld8(ts.tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(sg * g.RB + c8 * 8), v);
-          if (mine && sg == my_s) {
+      DBG(3);
+      const int k_l = lane / R, i_l = lane - k_l * R;
+      const bool valid = lane < spq;
+      const uint32_t tq = ts.tmem + ((uint32_t)(32 * qd) << 16), part_s = smem_u32(part);
+      int piece = 0;
+      for (int k = 0; k < SG / NQ; ++k) {
+        const int sg = qd + NQ * k;
+        const bool keep = valid && k == k_l;
+        const uint32_t pdst = part_s + (uint32_t)((sg * R + i_l) * g.RB) * 4u;
+        for (int col = 0; col < g.RB; ++piece) {
+          const int rem = g.RB - col;
+          const bool my_piece = (piece & 1) == half;
+          if (rem >= 32) {
+            if (my_piece) {
+              float v[32];
+              tc_ld32(tq + (uint32_t)(sg * g.RB + col), v);
+              if (keep) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) part[((c8 * 8 + j) * SG + sg) * R + my_i] = v[j];
+                for (int e = 0; e < 32; e += 4)
+                  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(pdst + (uint32_t)(col + e) * 4u), "f"(v[e]), "f"(v[e + 1]), "f"(v[e + 2]), "f"(v[e + 3]) : "memory");
+              }
+            }
+            col += 32;
+          } else if (rem >= 16) {
+            if (my_piece) {
+              float v[16];
+              tc_ld16(tq + (uint32_t)(sg * g.RB + col), v);
+              if (keep) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(pdst + (uint32_t)(col + e) * 4u), "f"(v[e]), "f"(v[e + 1]), "f"(v[e + 2]), "f"(v[e + 3]) : "memory");
+              }
+            }
+            col += 16;
+          } else {
+            if (my_piece) {
+              float v[8];
+              tc_ld8(tq + (uint32_t)(sg * g.RB + col), v);
+              if (keep) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 4)
+                  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(pdst + (uint32_t)(col + e) * 4u), "f"(v[e]), "f"(v[e + 1]), "f"(v[e + 2]), "f"(v[e + 3]) : "memory");
+              }
+            }
+            col += 8;
           }
         }
+      }
       tc_fence_before();
     }
   }
   ++ts.nacc;
   asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
+  DBG(4);
 
   if (e_on) {
     float v0 = 0.f, v1 = 0.f;                                  // segment partials summed in segment order
-    for (int sg = 0; sg < SG; ++sg) { v0 += part[(lr0 * SG + sg) * R + ei]; v1 += part[(lr1 * SG + sg) * R + ei]; }
+    for (int sg = 0; sg < SG; ++sg) { v0 += part[(sg * R + ei) * g.RB + lr0]; v1 += part[(sg * R + ei) * g.RB + lr1]; }
     if (EPI == EPI_RESID) {
       st_relaxed_u32(yt + (size_t)ei * a.ldy + en0, tag_word(pre_resid + rbf(v0), tag_out));
     } else if (EPI == EPI_STORE) {
@@ -1311,10 +1355,12 @@ __device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcG
       }
     } else {
       float u0 = 0.f;
-      if (cfg) for (int sg = 0; sg < SG; ++sg) u0 += part[(lr0 * SG + sg) * R + a.B + ei];
+      if (cfg) for (int sg = 0; sg < SG; ++sg) u0 += part[(sg * R + a.B + ei) * g.RB + lr0];
       gemv_epilogue<EPI>(a, ei, en0, en1, false, v0, 0.f, u0, 0.f);
     }
   }
+  DBG(5);
+#undef DBG
 }
 
 // K/V of the tokens cached by EARLIER steps for this CTA's first attention unit of the layer: issued before the
@@ -1615,7 +1661,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       unsigned long long* slot = MEGA_STAMP_SLOT();
       if (TC)
         mega_consume_tc<R, 1, PRO_NORM, EPI_QKV>(a, m.tg[TG_QKV], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
-                                                 nullptr, TAG(ph), nullptr, 0u, m.qt, m.kvt, slot, 1, &qkv_pre);
+                                                 nullptr, TAG(ph), nullptr, 0u, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
       else
       mega_consume<R, 2, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
                                                nullptr, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
@@ -1645,7 +1691,8 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
         if (last) {
           if (TC)
             mega_consume_tc<R, 1, PRO_NONE, EPI_RESID>(a, m.tg[TG_OUT], ring, part, full_bar, empty_bar, ts, red, S, g2, true, warp, lane, src,
-                                                       TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph_in - 1), nullptr, nullptr, slot, 0, nullptr);
+                                                       TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph_in - 1), nullptr, nullptr, slot, 0, nullptr,
+                                                       (stamping && li == 1) ? m.timeline + 208 : nullptr);
           else
           mega_consume<R, 2, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane, src, TAG(ph - 1), m.xt, TAG(ph),
                                                      m.xt, nullptr, nullptr, slot);
@@ -1670,7 +1717,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       unsigned long long* slot = MEGA_STAMP_SLOT();
       if (TC)
         mega_consume_tc<R, 1, PRO_NORM, EPI_SILU>(a, m.tg[TG_FC1], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
-                                                  m.ht, TAG(ph), nullptr, 0u, nullptr, nullptr, slot, 0, nullptr);
+                                                  m.ht, TAG(ph), nullptr, 0u, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 216 : nullptr);
       else
       mega_consume<R, 2, 4, PRO_NORM, EPI_SILU>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
                                                 nullptr, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 220 : nullptr);
@@ -1686,7 +1733,8 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
         // x was last written by the out_proj pass two phases back (phase ph - 2)
         if (m.F > 2048)
           mega_consume_tc<R, 4, PRO_NONE, EPI_RESID>(a, m.tg[TG_FC2], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.ht,
-                                                     TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph - 2), nullptr, nullptr, slot, 0, nullptr);
+                                                     TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph - 2), nullptr, nullptr, slot, 0, nullptr,
+                                                     (stamping && li == 1) ? m.timeline + 224 : nullptr);
         else
           mega_consume_tc<R, 1, PRO_NONE, EPI_RESID>(a, m.tg[TG_FC2], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.ht,
                                                      TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph - 2), nullptr, nullptr, slot, 0, nullptr);
@@ -2293,7 +2341,11 @@ size_t zb_mega_arena_bytes(const zb_model* model, int R) {
 }
 
 bool zb_mega_tc_enabled(const zb_model* model, int R) {
-  const int enabled = env_int("ZB_MEGA_TC", 1);              // 0: FFMA2 consumer (read per session: tests compare both in one process)
+  // Opt-in (read per session: tests compare both consumers in one process).  Measured on B200, full size, 200 frames:
+  // 1.21 ms per step against 1.06 for the FFMA2 consumer at batch 1, 1.55 against 1.43 at batch 2.  The streaming phases
+  // are HBM-bound with either consumer; what the tensor pipe saves there (fc1 9.2 -> 8.7 us) it loses in the fixed cost
+  // of every phase (activation image + CTA barrier 0.8 us, MMA tail 0.5, accumulator read-back 0.5 against registers only).
+  const int enabled = env_int("ZB_MEGA_TC", 0);
   MegaTcPlan p;
   return enabled && mega_tc_plan(model->d, model->ctx->num_sms, R, &p);
 }

@@ -288,14 +288,21 @@ __device__ __forceinline__ void tc_issue(const TcArgs& a, const TcGemm& g, unsig
   const int S = a.stages, SB = a.bstages, n = u.kb1 - u.kb0;
   const uint32_t idesc = make_idesc(128, a.Rp);
   const bool lane0 = (threadIdx.x & 31) == 0;
-  // the whole warp walks the rings on warp-uniform values, one elected lane issues (tc.cuh: elect_one)
-  for (int j = 0; j < n; j += kKbSlot, ++gst, ++bst) {
+  // the whole warp walks the rings on warp-uniform values, one elected lane issues (tc.cuh: elect_one).  Ring positions
+  // advance by increments: a division per slot on this single warp's dependent instruction chain costs as much as the MMAs.
+  int slot = gst % S, use = gst / S, bslot = bst % SB, buse = bst / SB;
+  const uint32_t ring0 = smem_u32(ring), bring0 = smem_u32(bring);
+  for (int j = 0; j < n; j += kKbSlot) {
     const int cnt = min(kKbSlot, n - j);
-    const int slot = gst % S, bslot = bst % SB;
-    mbar_wait(&bfull[bslot], (uint32_t)((bst / SB) & 1));
-    ring_wait_full(full_bar, slot_use, S, gst, lane0);
+    mbar_wait(&bfull[bslot], (uint32_t)(buse & 1));
+    if (use > 0) {
+      for (unsigned spins = 0; slot_use[slot] < use - 1; ++spins)
+        if (spins > (1u << 26)) asm volatile("trap;");
+    }
+    mbar_wait(&full_bar[slot], (uint32_t)(use & 1));
+    if (lane0) slot_use[slot] = use;
     tc_fence_after();
-    const uint32_t ra = smem_u32(ring + (size_t)slot * kSlot), rb = smem_u32(bring + (size_t)bslot * a.bslot_bytes);
+    const uint32_t ra = ring0 + (uint32_t)slot * kSlot, rb = bring0 + (uint32_t)bslot * (uint32_t)a.bslot_bytes;
     if (elect_one()) {
       for (int e = 0; e < cnt; ++e) {
         const uint64_t da = make_smem_desc(ra + (uint32_t)e * (kSlot / kKbSlot));
@@ -308,7 +315,10 @@ __device__ __forceinline__ void tc_issue(const TcArgs& a, const TcGemm& g, unsig
       tc_commit(&bempty[bslot]);
     }
     __syncwarp();
+    if (++slot == S) { slot = 0; ++use; }
+    if (++bslot == SB) { bslot = 0; ++buse; }
   }
+  gst += (n + kKbSlot - 1) / kKbSlot; bst += (n + kKbSlot - 1) / kKbSlot;
   if (elect_one()) tc_commit(acc_full);
   __syncwarp();
 }

@@ -212,7 +212,7 @@ def run_b200(args):
     N, Lc, P = args.frames, args.cond_len, args.prefix_frames
 
     # every rank builds the same replica (seeded CPU generator) - no weight broadcast needed for synthetic runs
-    dacw = make_dac_weights(seed=1)
+    dacw = make_dac_weights(seed=1, with_encoder=P > 0)        # configs[4]: the audio prefix is ENCODED on the device, too
     autoenc = DACAutoencoder(dacw, device=dev)
 
     def build(variant):
@@ -256,8 +256,10 @@ def run_b200(args):
         cond_dev = cond_host.to(dev)
         prefix_host = prefix_dev = None
         if P:
-            prefix_host = torch.randint(0, 1024, (B, 9, P), generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
-            prefix_dev = prefix_host.to(dev)
+            # synthetic prefix AUDIO (P frames = P * 512 samples at 44.1 kHz); value: its codes are resident, e2e: the waveform
+            # comes from pinned host memory and is encoded (autoencoder.encode) inside the timed region
+            prefix_host = (0.1 * torch.randn(B, 1, P * 512, generator=torch.Generator().manual_seed(7 + rank))).pin_memory()
+            prefix_dev = model.autoencoder.encode(prefix_host.to(dev))
         wav_host = torch.empty((B, 1, 512 * (P + N)), dtype=torch.float32).pin_memory()
 
         def gen(c, pfx, n_frames, seed):
@@ -270,7 +272,7 @@ def run_b200(args):
 
         def step_e2e(seed):
             c = cond_host.to(dev, non_blocking=True)                       # H2D inside the timed region
-            pfx = prefix_host.to(dev, non_blocking=True) if P else None
+            pfx = model.autoencoder.encode(prefix_host.to(dev, non_blocking=True)) if P else None
             codes = gen(c, pfx, N, seed)
             wav = model.autoencoder.decode(codes)
             wav_host[..., : wav.shape[-1]].copy_(wav, non_blocking=True)   # D2H of the result
@@ -363,7 +365,7 @@ def run_b200(args):
             steps_full = N + 8
             breakdown = {"decode_ms": step_ms * steps_full, "prefill_and_setup_ms": max(0.0, t_full - step_ms * steps_full), "dac_ms": dac_ms}
         return {"value": value, "ms_per_step": ms / steps, "frames_per_second": frames / (ms / 1e3), "launches": int(launches),
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cond_host.numel() * 2, "d2h_bytes_per_step": wav_host.numel() * 4,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cond_host.numel() * 2 + (prefix_host.numel() * 4 if P else 0), "d2h_bytes_per_step": wav_host.numel() * 4,
                         "ms_per_step": ms_e / steps},
                 "clocks": clock_info, "roofline": roof, "breakdown_ms": breakdown, "cond_dev": cond_dev}
 

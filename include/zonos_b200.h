@@ -237,6 +237,29 @@ ZB_API zb_status zb_dac_destroy(zb_dac* dac);
 ZB_API zb_status zb_dac_decode(zb_ctx* ctx, const zb_dac* dac, const int64_t* codes, int32_t B, int32_t T, float* wav,
                         zb_stream stream);
 
+/* ------------------------------------------------------------------ DAC encoder -------------- */
+/* Weights of transformers.DacModel (encode side), fp32 device pointers in module order, BORROWED for the call only:
+ * encoder.conv1 {weight, bias}; per block: 3 x res_unit {snake1.alpha, conv1.weight, conv1.bias, snake2.alpha, conv2.weight,
+ * conv2.bias}, snake1.alpha, conv1 {weight, bias}; encoder.snake1.alpha, encoder.conv2 {weight, bias}; per codebook:
+ * in_proj {weight, bias}, codebook.weight, out_proj {weight, bias}  (zonos_b200/autoencoder.py:dac_encoder_tensor_order). */
+typedef struct {
+  int32_t n_codebooks, codebook_size, codebook_dim, latent_dim;    /* 9, 1024, 8, 1024 */
+  int32_t hidden;               /* 64 */
+  int32_t n_blocks;             /* 4 */
+  int32_t strides[8];           /* 2,4,8,8 */
+  const float* const* tensors;  /* HOST array of device pointers */
+  int32_t n_tensors;
+  int32_t _pad;
+} zb_dac_enc_desc;
+
+/* Replaces DACAutoencoder.encode (zonos/autoencoder.py:104-117 -> transformers modeling_dac.py:581-640, :442-473, :281-343):
+ * wav fp32 [B, 1, L] at 44.1 kHz, L a multiple of 512 (what `preprocess`, autoencoder.py:80-100, returns) -> codes int64
+ * [B, Q, L/512].  fp32 throughout like the reference (no autocast on this path).  `workspace` is caller-owned device
+ * memory of at least zb_dac_encode_workspace_bytes(B, L) bytes. */
+ZB_API size_t zb_dac_encode_workspace_bytes(int32_t B, int64_t L);
+ZB_API zb_status zb_dac_encode(zb_ctx* ctx, const zb_dac_enc_desc* desc, const float* wav, int32_t B, int64_t L, int64_t* codes,
+                        void* workspace, size_t workspace_bytes, zb_stream stream);
+
 /* ------------------------------------------------------------------ diagnostics -------------- */
 /* Launches ONE production decode kernel `iters` times back to back (layer, layer+1, ... cyclically, so every launch
  * streams its weights from HBM) on scratch activations with `rows` activation rows (1..8), so a benchmark can time it

@@ -249,6 +249,29 @@ def golden_dac():
     np.savez_compressed(os.path.join(HERE, "dac_decode.npz"), codes=codes.numpy(), wav=wav.numpy())
 
 
+# ---------------------------------------------------------------- DAC encode (audio prefix -> codes)
+def golden_dac_encode():
+    """`DACAutoencoder.encode` (zonos/autoencoder.py:104-117) = transformers' `DacModel.encode(wav).audio_codes` in fp32, on
+    seeded encoder weights and a seeded waveform of 12 frames (2 utterances)."""
+    w = make_dac_weights(seed=1, with_encoder=True)
+    ae = ref_ae.DACAutoencoder()
+    missing = ae.dac.load_state_dict(w, strict=False)
+    assert not missing.missing_keys and not missing.unexpected_keys, missing
+    g = torch.Generator().manual_seed(8)
+    t = torch.arange(12 * 512) / 44100.0
+    wav = torch.stack([0.4 * torch.sin(2 * math.pi * 220 * t) + 0.05 * torch.randn(t.shape, generator=g),
+                       0.3 * torch.sin(2 * math.pi * 523 * t) * torch.sin(2 * math.pi * 3 * t) + 0.05 * torch.randn(t.shape, generator=g)]).unsqueeze(1)
+    codes = ae.encode(wav)
+    z = ae.dac.encoder(wav)
+    mine_z = o_dac.encode_latents(w, wav)
+    margins = []
+    mine = o_dac.quantize(w, mine_z, margins)
+    print("dac encode: codes", tuple(codes.shape), "latent absmax", z.abs().max().item(), "oracle latent err", (mine_z - z).abs().max().item(),
+          "codes equal", bool(torch.equal(mine, codes)), "smallest margin", min(m.min().item() for m in margins))
+    assert codes.shape == (2, 9, 12) and torch.equal(mine, codes) and torch.equal(mine_z, z)
+    np.savez_compressed(os.path.join(HERE, "dac_encode.npz"), wav=wav.numpy(), codes=codes.numpy(), latents=z.numpy())
+
+
 # ---------------------------------------------------------------- prefix conditioner (tensor conditioners)
 COND_CFG = dict(projection="linear", conditioners=[
     dict(type="PassthroughConditioner", name="speaker", cond_dim=128, uncond_type="learned", projection="linear"),
@@ -290,4 +313,5 @@ if __name__ == "__main__":
     golden_sampler()
     golden_generate()
     golden_dac()
+    golden_dac_encode()
     print("golden fixtures written to", HERE)

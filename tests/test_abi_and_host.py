@@ -156,3 +156,32 @@ def test_shipped_configs_load():
     assert c.backbone.n_layer == hybrid_config_dict()["backbone"]["n_layer"] and c.backbone.ssm_cfg == {"layer": "Mamba2"}
     t = ZonosConfig.from_dict(json.load(open(os.path.join(root, "zonos_v0.1_transformer.json"))))
     assert t.backbone.n_layer == 26 and t.backbone.attn_layer_idx == list(range(26))
+
+
+def test_from_local_reads_a_reference_format_checkpoint(tmp_path):
+    """zonos/model.py:128-176: `config.json` + `model.safetensors` as the reference's checkpoints store them - one
+    `heads.{i}.weight` per codebook (fused row-wise on load, model.py:208-223), embedding tables with 1026 rows (padded to the
+    multiple of 8 the module holds, model.py:164-172), bf16 tensors.  Loaded on the CPU here (state-dict plumbing only; the
+    compute path has no CPU kernels)."""
+    import json
+    import safetensors.torch
+    from zonos_b200 import Zonos, transformer_config_dict
+    from zonos_b200.synthetic import TINY_DIMS, make_backbone_weights
+    w = make_backbone_weights(**TINY_DIMS, seed=21)
+    ckpt = {k: v.clone() for k, v in w.items() if k.startswith("backbone.")}
+    fused = w["fused_heads.weight"]
+    for i in range(9):
+        ckpt[f"heads.{i}.weight"] = fused[i * 1025:(i + 1) * 1025].clone().contiguous()
+        ckpt[f"embeddings.{i}.weight"] = w[f"embeddings.{i}.weight"][:1026].clone().contiguous()
+    cfg_path, st_path = tmp_path / "config.json", tmp_path / "model.safetensors"
+    cfg_path.write_text(json.dumps(transformer_config_dict(**TINY_DIMS)))
+    safetensors.torch.save_file(ckpt, str(st_path))
+    m = Zonos.from_local(str(cfg_path), str(st_path), device="cpu")
+    sd = m.state_dict()
+    assert sd["fused_heads.weight"].dtype == torch.bfloat16 and torch.equal(sd["fused_heads.weight"], fused)
+    for i in range(9):
+        e = sd[f"embeddings.{i}.weight"]
+        assert e.shape[0] == 1032 and torch.equal(e[:1026], w[f"embeddings.{i}.weight"][:1026]) and not e[1026:].any()
+    for k, v in w.items():
+        if k.startswith("backbone."):
+            assert torch.equal(sd[k], v), k

@@ -319,6 +319,36 @@ def test_dac_decode_matches_reference_golden():
     assert err2.max() < 2.5 * noise.max() and err2.mean() < 2.5 * noise.mean(), (err2.max(), err2.mean(), noise.max(), noise.mean())
 
 
+def test_dac_encode_matches_reference_golden_and_oracle():
+    """Audio-prefix path (zonos/autoencoder.py:104-117): native fp32 encoder + residual VQ.  (a) the reference-recorded
+    fixture: every code equal; (b) one second of noisy audio, two utterances: codes equal to the oracle's wherever the
+    oracle's decision has a margin above fp32 summation noise, and the codes decode back to (nearly) the same latents."""
+    from zonos_b200 import DACAutoencoder
+    g = load_golden("dac_encode.npz")
+    w = make_dac_weights(seed=1, with_encoder=True)
+    ae = DACAutoencoder(w, device=DEV)
+    codes = ae.encode(torch.from_numpy(g["wav"]).to(DEV))
+    assert codes.dtype == torch.int64 and codes.shape == g["codes"].shape
+    assert np.array_equal(codes.cpu().numpy(), g["codes"])
+    gen = torch.Generator().manual_seed(31)
+    L = 86 * 512
+    t = torch.arange(L) / 44100.0
+    wav = torch.stack([0.3 * torch.sin(2 * math.pi * 180 * t) + 0.1 * torch.randn(L, generator=gen),
+                       0.5 * torch.sin(2 * math.pi * 700 * t) * torch.sin(2 * math.pi * 5 * t) + 0.02 * torch.randn(L, generator=gen)]).unsqueeze(1)
+    got = ae.encode(wav.to(DEV)).cpu()
+    margins = []
+    ref = o_dac.quantize(w, o_dac.encode_latents(w, wav), margins)
+    margin = torch.stack(margins, dim=1)                       # [B, Q, T]
+    # a flipped decision changes the residual the later codebooks of that frame see: compare up to the first near-tie
+    for b in range(2):
+        for f in range(ref.shape[2]):
+            for q in range(9):
+                if margin[b, q, f] < 1e-4:
+                    break
+                assert got[b, q, f] == ref[b, q, f], (b, q, f, float(margin[b, q, f]))
+    assert (got == ref).float().mean() > 0.99
+
+
 @pytest.mark.parametrize("gain", [0.8, 1.0])
 def test_dac_decode_unsaturated_is_tight(gain):
     """The golden fixture's random-init decoder (gain 1.3) saturates tanh, which could hide a wrong tap or phase in one

@@ -62,6 +62,21 @@ def test_generate_matches_reference(name):
         assert np.array_equal(trace["logits"][int(step)].numpy(), g["logits"][j])      # bit-identical on CPU
 
 
+def test_dac_encode_matches_reference():
+    """`DACAutoencoder.encode` of the reference (transformers `DacModel.encode`, fp32) on the seeded encoder: the oracle's
+    latents are bit-identical to the recorded ones on the CPU and every code index is equal."""
+    g = load_golden("dac_encode.npz")
+    w = make_dac_weights(seed=1, with_encoder=True)
+    wav = torch.from_numpy(g["wav"])
+    z = o_dac.encode_latents(w, wav)
+    assert np.abs(z.numpy() - g["latents"]).max() < 1e-5
+    margins = []
+    codes = o_dac.quantize(w, torch.from_numpy(g["latents"]), margins)
+    assert np.array_equal(codes.numpy(), g["codes"]) and codes.dtype == torch.int64
+    assert np.array_equal(o_dac.encode(w, wav).numpy(), g["codes"])
+    assert min(m.min().item() for m in margins) > 1e-4        # the fixture holds no decision within fp32 summation noise
+
+
 def test_dac_decode_matches_reference():
     g = load_golden("dac_decode.npz")
     wav = o_dac.decode(make_dac_weights(seed=1), torch.from_numpy(g["codes"]))

@@ -57,6 +57,11 @@ class zb_dac_desc(C.Structure):
         ("strides", c_int32 * 8), ("tensors", C.POINTER(c_void_p)), ("n_tensors", c_int32), ("_pad", c_int32)]
 
 
+class zb_dac_enc_desc(C.Structure):
+    _fields_ = [(n, c_int32) for n in ("n_codebooks", "codebook_size", "codebook_dim", "latent_dim", "hidden", "n_blocks")] + [
+        ("strides", c_int32 * 8), ("tensors", C.POINTER(c_void_p)), ("n_tensors", c_int32), ("_pad", c_int32)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/zonos_b200.h
 PROTOTYPES = {
     "zb_abi_version": (c_int32, []),
@@ -80,6 +85,8 @@ PROTOTYPES = {
     "zb_dac_create": (c_int32, [c_void_p, C.POINTER(zb_dac_desc), C.POINTER(c_void_p), c_void_p]),
     "zb_dac_destroy": (c_int32, [c_void_p]),
     "zb_dac_decode": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "zb_dac_encode_workspace_bytes": (C.c_size_t, [c_int32, c_int64]),
+    "zb_dac_encode": (c_int32, [c_void_p, C.POINTER(zb_dac_enc_desc), c_void_p, c_int32, c_int64, c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "zb_bench_kernel": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
 }
 

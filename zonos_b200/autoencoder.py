@@ -1,7 +1,7 @@
 """DAC 44.1 kHz autoencoder front-end with the reference's surface (`zonos/autoencoder.py:49-170`):
 `decode(codes[B,9,T]) -> wav[B,1,512*T]` runs in libzonos_b200.so; `sampling_rate`, `num_codebooks`,
-`codebook_size` are the attributes callers read.  `encode` / `preprocess` (SURVEY.md 8(f) "next") stay on the
-`transformers` DacModel when one is attached."""
+`codebook_size` are the attributes callers read.  `encode(wav[B,1,L]) -> codes[B,9,L/512]` (the audio-prefix path, SURVEY.md
+8(f)) runs there too when the state dict carries the encoder tensors; `preprocess` is the reference's torchaudio resample."""
 import ctypes as C
 import math
 
@@ -29,6 +29,22 @@ def dac_tensor_order(n_codebooks=9, n_blocks=4) -> list[str]:
     return keys
 
 
+def dac_encoder_tensor_order(n_codebooks=9, n_blocks=4) -> list[str]:
+    """state_dict keys in the order zb_dac_enc_desc.tensors expects (include/zonos_b200.h)."""
+    keys = ["encoder.conv1.weight", "encoder.conv1.bias"]
+    for i in range(n_blocks):
+        p = f"encoder.block.{i}."
+        for j in (1, 2, 3):
+            r = p + f"res_unit{j}."
+            keys += [r + "snake1.alpha", r + "conv1.weight", r + "conv1.bias", r + "snake2.alpha", r + "conv2.weight", r + "conv2.bias"]
+        keys += [p + "snake1.alpha", p + "conv1.weight", p + "conv1.bias"]
+    keys += ["encoder.snake1.alpha", "encoder.conv2.weight", "encoder.conv2.bias"]
+    for k in range(n_codebooks):
+        p = f"quantizer.quantizers.{k}."
+        keys += [p + "in_proj.weight", p + "in_proj.bias", p + "codebook.weight", p + "out_proj.weight", p + "out_proj.bias"]
+    return keys
+
+
 class DACAutoencoder:
     def __init__(self, state_dict: dict | None = None, device="cuda", dac_module=None):
         """state_dict: DacModel tensors (decode side).  None -> `DacModel.from_pretrained("descript/dac_44khz")`
@@ -44,6 +60,10 @@ class DACAutoencoder:
         self.device = torch.device(device)
         self._handle = None
         self._create(state_dict)
+        # encode side (fp32 tensors kept on the device; the library borrows them per call)
+        ekeys = dac_encoder_tensor_order(self.num_codebooks, len(DAC_STRIDES))
+        self._enc_weights = [state_dict[k].detach().to(self.device, torch.float32).contiguous() for k in ekeys] \
+            if all(k in state_dict for k in ekeys) else None
 
     def _create(self, sd: dict):
         ctx = _lib.context(self.device)
@@ -79,9 +99,12 @@ class DACAutoencoder:
         return torch.nn.functional.pad(wav, (left, 0), value=0)
 
     def encode(self, wav: torch.Tensor) -> torch.Tensor:
-        if self.dac is None:
-            raise RuntimeError("encode needs a transformers DacModel (pass dac_module=...); only decode runs natively")
-        return self.dac.encode(wav).audio_codes
+        """zonos/autoencoder.py:104-117: preprocessed fp32 wav [B,1,L] (L a multiple of 512) -> int64 codes [B,Q,L/512]."""
+        if self._enc_weights is None:
+            raise RuntimeError("encode needs the encoder tensors (`encoder.*`, `quantizer.quantizers.*.in_proj.*`) in the state dict "
+                               "this DACAutoencoder was built from")
+        assert wav.dim() == 3 and wav.shape[1] == 1 and wav.shape[-1] % 512 == 0, "expected [B, 1, L] with L a multiple of 512 (preprocess)"
+        return torch.ops.zonos_b200.dac_encode(wav.to(self.device), self._enc_weights, self.num_codebooks)
 
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
         """zonos/autoencoder.py:119-140: int64 [B,Q,T] -> fp32 [B,1,512*T]."""

@@ -36,10 +36,15 @@ def tokenize_phonemes(phonemes: list[str]) -> tuple[torch.Tensor, list[int]]:
 
 def _spell_numbers(text: str) -> str:
     """Digits -> words where `inflect` is available (the reference's number normalisation, conditioning.py:199-221)."""
+    if not re.search(r"[0-9]", text):
+        return text
     try:
         import inflect
-    except ImportError:
-        return text
+    except ImportError as e:
+        # never diverge silently: without the number normalisation eSpeak would read the digits its own way and the
+        # conditioning would differ from the reference's for the same text
+        raise RuntimeError("text with digits needs the `inflect` package for the reference's number normalisation "
+                           "(zonos/conditioning.py:199-221); spell the numbers out or install it") from e
     eng = inflect.engine()
     text = re.sub(r"([0-9][0-9,]+[0-9])", lambda m: m.group(1).replace(",", ""), text)
     text = re.sub(r"£([0-9,]*[0-9]+)", r"\1 pounds", text)

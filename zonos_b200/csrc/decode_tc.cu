@@ -377,7 +377,7 @@ __device__ __forceinline__ void tc_epi_silu_direct(const TcArgs& a, const TcGemm
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const float yv = rbf(sbuf[(i + e) * ld + m]), gg = rbf(sbuf[(g.RBv + i + e) * ld + m]);
-      const float sg = rbf(gg / (1.0f + expf(-gg)));                  // F.silu on bf16: fp32 math, bf16 result
+      const float sg = rbf(gg / (1.0f + expf(-gg)));                  // F.silu on bf16: fp32 math, bf16 result (fast ex2/rcp: 1 % of the step, not taken)
       r2[e] = __fmul_rn(yv, sg);
     }
     *reinterpret_cast<uint32_t*>(a.h + (size_t)m * a.F + (size_t)u.rb * g.RBv + i) = pack_bf16(r2[0], r2[1]);

@@ -14,6 +14,7 @@ and `zonos/model.py:179-234`.  There is no CPU implementation: 
                                             heads/CFG + sampler + EOS/delay bookkeeping, zonos/model.py:439-509)
                                                                             -> zb_generate_steps
     torch.ops.zonos_b200.dac_decode         zonos/autoencoder.py:119-140    -> zb_dac_decode
+    torch.ops.zonos_b200.dac_encode         zonos/autoencoder.py:104-117    -> zb_dac_encode
 """
 import ctypes as C
 from typing import List, Optional
@@ -153,4 +154,32 @@ def _(dac, codes, upsample):
     return codes.new_empty((B, 1, upsample * T), dtype=torch.float32)
 
 
-OPS = ("embed_codes", "backbone_forward", "heads_cfg", "sample_update", "decode_step", "dac_decode")
+@custom_op("zonos_b200::dac_encode", mutates_args=())
+def dac_encode(wav: torch.Tensor, weights: List[torch.Tensor], n_codebooks: int) -> torch.Tensor:
+    """fp32 [B,1,L] at 44.1 kHz (L a multiple of 512) -> int64 [B,Q,L/512]: DAC encoder convs + residual vector quantiser in
+    fp32 (zonos/autoencoder.py:104-117).  `weights`: the fp32 tensors in the order of `autoencoder.dac_encoder_tensor_order`."""
+    _cuda(wav, "dac_encode")
+    B, _, L = wav.shape
+    wav = wav.to(torch.float32).contiguous()
+    codes = torch.empty((B, n_codebooks, L // 512), dtype=torch.int64, device=wav.device)
+    ctx = _lib.context(wav.device)
+    arr = (C.c_void_p * len(weights))(*[t.data_ptr() for t in weights])
+    d = _lib.zb_dac_enc_desc()
+    d.n_codebooks, d.codebook_size, d.codebook_dim, d.latent_dim, d.hidden, d.n_blocks = n_codebooks, 1024, 8, 1024, 64, 4
+    for i, s_ in enumerate((2, 4, 8, 8)):
+        d.strides[i] = s_
+    d.tensors, d.n_tensors = arr, len(weights)
+    nbytes = int(ctx.lib.zb_dac_encode_workspace_bytes(B, L))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=wav.device)
+    with ctx.lock:
+        ctx.check(ctx.lib.zb_dac_encode(ctx.handle, C.byref(d), _lib.ptr(wav), B, L, _lib.ptr(codes), _lib.ptr(ws), nbytes, _lib.stream_ptr(wav.device)))
+    return codes
+
+
+@dac_encode.register_fake
+def _(wav, weights, n_codebooks):
+    B, _, L = wav.shape
+    return wav.new_empty((B, n_codebooks, L // 512), dtype=torch.int64)
+
+
+OPS = ("embed_codes", "backbone_forward", "heads_cfg", "sample_update", "decode_step", "dac_decode", "dac_encode")

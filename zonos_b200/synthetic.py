@@ -53,8 +53,12 @@ def make_backbone_weights(d_model=2048, n_layer=26, n_heads=16, n_heads_kv=4, d_
     return w
 
 
-def make_dac_weights(seed=1, dtype=torch.float32, n_codebooks=9, gain=1.3) -> dict:
-    """Decode-side DacModel(DacConfig(sampling_rate=44100)) tensors (quantizer tables + decoder)."""
+DAC_ENC_STRIDES = (2, 4, 8, 8)
+
+
+def make_dac_weights(seed=1, dtype=torch.float32, n_codebooks=9, gain=1.3, with_encoder=False) -> dict:
+    """DacModel(DacConfig(sampling_rate=44100)) tensors: quantizer tables + decoder; with_encoder adds the encoder and the
+    quantizers' in_proj (drawn from a second generator, so the decode-side tensors do not depend on the flag)."""
     g = torch.Generator().manual_seed(seed)
     w = {}
 
@@ -84,6 +88,25 @@ def make_dac_weights(seed=1, dtype=torch.float32, n_codebooks=9, gain=1.3) -> di
             conv(r + "conv2", ch, ch, 1)
     w["decoder.snake1.alpha"] = (0.5 + torch.rand(1, ch, 1, generator=g)).to(dtype)
     conv("decoder.conv2", 1, ch, 7)
+    if with_encoder:
+        g = torch.Generator().manual_seed(seed + 1000)        # (conv() draws from `g`)
+        for k in range(n_codebooks):
+            conv(f"quantizer.quantizers.{k}.in_proj", 8, 1024, 1)
+        conv("encoder.conv1", 64, 1, 7)
+        ch = 64
+        for i, s in enumerate(DAC_ENC_STRIDES):
+            p = f"encoder.block.{i}."
+            for j in (1, 2, 3):
+                r = p + f"res_unit{j}."
+                w[r + "snake1.alpha"] = (0.5 + torch.rand(1, ch, 1, generator=g)).to(dtype)
+                conv(r + "conv1", ch, ch, 7)
+                w[r + "snake2.alpha"] = (0.5 + torch.rand(1, ch, 1, generator=g)).to(dtype)
+                conv(r + "conv2", ch, ch, 1)
+            w[p + "snake1.alpha"] = (0.5 + torch.rand(1, ch, 1, generator=g)).to(dtype)
+            conv(p + "conv1", 2 * ch, ch, 2 * s)
+            ch *= 2
+        w["encoder.snake1.alpha"] = (0.5 + torch.rand(1, ch, 1, generator=g)).to(dtype)
+        conv("encoder.conv2", 1024, ch, 3)
     return w
 
 

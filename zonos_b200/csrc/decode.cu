@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a) {
 }
 
 // ------------------------------------------------------------------ skinny GEMM (GEMV family) -
-enum { PRO_NONE = 0, PRO_NORM = 1 };
+enum { PRO_NONE = 0, PRO_NORM = 1, PRO_GATED = 2 };           // GATED: mamba_ssm RMSNormGated of y * silu(z) (persistent kernel only)
 enum { EPI_STORE = 0, EPI_RESID = 1, EPI_QKV = 2, EPI_SILU = 3, EPI_HEADS = 4 };
 
 struct GemvArgs {
@@ -706,6 +706,8 @@ __global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
 // ================================================================================================================
 struct MegaLayer {
   const bf16 *norm_w, *norm_b, *in_proj, *out_proj, *norm2_w, *norm2_b, *fc1, *fc2; bf16* kv_layer;
+  // Mamba2 layers (kind 1): conv1d / SSM parameters, gated-norm weight, this layer's recurrent state of all rows
+  const bf16 *conv_w, *conv_b, *dt_bias, *A_log, *Dp, *mnorm_w; bf16 *conv_state, *ssm_state; long long kind;
   const bf16 *in_t, *out_t, *fc1_t, *fc2_t;                   // the same matrices re-laid out for the tcgen05 consumer (see MegaTcGeo)
 };
 // tcgen05 consumer: a matrix [N, K] is cut into units of RB weight rows (a multiple of 8; fc1: RBv value rows followed by
@@ -736,6 +738,8 @@ struct MegaArgs {
   unsigned long long* steplog;    // debug: [2*step] start, [2*step+1] end of every step (CTA 0)
   // tcgen05 consumer (decode_step_kernel<R, true>)
   const bf16* heads_t; MegaTcGeo tg[TG_COUNT];
+  // hybrid stacks: Mamba2 layers run as three phases (in_proj, conv1d step + state update, gated norm + out_proj)
+  int nph, d_inner, m_nheads, ipo, conv_dim; uint32_t *zxt, *ygt;
 };
 
 constexpr int kMegaStageBytes = 32 * 1024, kMegaAttnBytes = 40 * 1024;
@@ -838,7 +842,8 @@ template <int R, int NC, int RW, int PRO, int EPI>
 __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* ring, float* part, uint64_t* full_bar, uint64_t* empty_bar,
                                              float (*red)[kMW][4], int S, int& gst, bool release, int warp, int lane,
                                              const uint32_t* xt, uint32_t tag_in, uint32_t* yt, uint32_t tag_out, const uint32_t* rt, uint32_t* qt,
-                                             uint32_t* kvt, unsigned long long* stamp, int norm_pending = 0, const MegaQkvPre* qkv_pre = nullptr, unsigned long long* dbg = nullptr) {
+                                             uint32_t* kvt, unsigned long long* stamp, int norm_pending = 0, const MegaQkvPre* qkv_pre = nullptr, unsigned long long* dbg = nullptr,
+                                             const uint32_t* zt = nullptr, int ldz = 0, uint32_t tag_z = 0u) {
 #define DBG(i) do { if (dbg && threadIdx.x == 0) dbg[i] = gtime(); } while (0)
   constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
   constexpr int Kc = NC * 256;
@@ -867,9 +872,40 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
     if (ok) break;
     if (spins > kMegaSpinLimit) asm volatile("trap;");
   }
+  if (PRO == PRO_GATED) {
+    // mamba_ssm RMSNormGated (norm_before_gate = False): g = y * silu(z) in fp32 from the bf16 y (this phase's input) and the
+    // bf16 z columns of the in_proj output (tagged by that earlier phase), xn = bf16(g * rsqrt(mean(g^2) + 1e-5) * w)
+    for (unsigned spins = 0;; ++spins) {
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t* src = zt + (size_t)i * ldz + koff + c * 256 + lane * 8;
+          const uint4 v0 = ld_relaxed_v4(src), v1 = ld_relaxed_v4(src + 4);
+          ok = ok && tags_ok(v0, tag_z) && tags_ok(v1, tag_z);
+          const float zz[8] = {untag(v0.x), untag(v0.y), untag(v0.z), untag(v0.w), untag(v1.x), untag(v1.y), untag(v1.z), untag(v1.w)};
+          if (ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xf[i][c * 8 + e] = xf[i][c * 8 + e] * (zz[e] / (1.0f + expf(-zz[e])));
+          }
+        }
+      if (ok) break;                                            // (a failed round leaves some xf scaled: reload them)
+      if (spins > kMegaSpinLimit) asm volatile("trap;");
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t* src = xt + (size_t)i * a.ldx + koff + c * 256 + lane * 8;
+          const uint4 v0 = ld_relaxed_v4(src), v1 = ld_relaxed_v4(src + 4);
+          xf[i][c * 8 + 0] = untag(v0.x); xf[i][c * 8 + 1] = untag(v0.y); xf[i][c * 8 + 2] = untag(v0.z); xf[i][c * 8 + 3] = untag(v0.w);
+          xf[i][c * 8 + 4] = untag(v1.x); xf[i][c * 8 + 5] = untag(v1.y); xf[i][c * 8 + 6] = untag(v1.z); xf[i][c * 8 + 7] = untag(v1.w);
+        }
+    }
+  }
   if (stamp && threadIdx.x == 0) *stamp = gtime();
   DBG(0);
-  if (PRO == PRO_NORM) {
+  if (PRO == PRO_NORM || PRO == PRO_GATED) {
     float mean[R], rstd[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) {
@@ -896,9 +932,10 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
       const float tot = warp_sum(lane < KS ? red[0][lane][i] : 0.f);
       const float tsq = warp_sum(lane < KS ? red[1][lane][i] : 0.f);
       const float mu = tot * inv_k;
-      mean[i] = (a.norm_kind == ZB_NORM_LAYERNORM) ? mu : 0.f;
-      const float var = (a.norm_kind == ZB_NORM_LAYERNORM) ? fmaxf(tsq * inv_k - mu * mu, 0.f) : tsq * inv_k;
-      rstd[i] = rsqrtf(var + a.eps);
+      const bool ln = PRO == PRO_NORM && a.norm_kind == ZB_NORM_LAYERNORM;     // (the gated norm is an RMS norm with its own eps)
+      mean[i] = ln ? mu : 0.f;
+      const float var = ln ? fmaxf(tsq * inv_k - mu * mu, 0.f) : tsq * inv_k;
+      rstd[i] = rsqrtf(var + (PRO == PRO_GATED ? 1e-5f : a.eps));
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -1511,6 +1548,91 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
   asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");       // scratch free for the next unit
 }
 
+// One Mamba2 unit of the persistent kernel = (activation row r, head hh): causal-conv1d step over the head's 64 x channels and
+// the shared 128 B + 128 C channels, selective state update of the head's [64 x 128] state (32 values per thread, in
+// registers), y = C.h + D x.  Same arithmetic as mamba_scan_kernel with T = 1 (mamba_ssm causal_conv1d_update +
+// selective_state_update, reached from zonos/backbone/_mamba_ssm.py:45-58).  Inputs: tagged words of the in_proj output
+// row (z | xBC | dt); output: y as tagged bf16 words - the gate y * silu(z) is applied by the out_proj prologue (PRO_GATED),
+// which keeps the product in fp32 like RMSNormGated does.
+__device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLayer& L, int unit, unsigned char* scratch, uint32_t tag_in, uint32_t tag_out,
+                                               unsigned long long* stamp) {
+  constexpr int P = 64, N = 128, DC = 4, CH = P + 2 * N;
+  float (*win)[DC] = reinterpret_cast<float (*)[DC]>(scratch);                 // [CH][DC] rolling window, oldest first
+  float (*cw)[DC] = reinterpret_cast<float (*)[DC]>(scratch + CH * DC * 4);
+  float* cb = reinterpret_cast<float*>(scratch + 2 * CH * DC * 4);
+  float* cout = cb + CH;
+  const int tid = threadIdx.x, r = unit / m.m_nheads, hh = unit % m.m_nheads;
+  const int p = tid >> 2, quarter = tid & 3;
+  auto chan = [&](int c) { return c < P ? hh * P + c : m.d_inner + (c - P); };   // index into xBC / conv_state
+  // state of earlier steps: does not depend on this step's activations, so it is fetched before the inputs are polled
+  for (int c = tid; c < CH; c += kMW * 32) {
+    const int gc = chan(c);
+    const uint2 wv = *reinterpret_cast<const uint2*>(L.conv_state + ((size_t)r * m.conv_dim + gc) * DC);
+    const uint2 cv = __ldg(reinterpret_cast<const uint2*>(L.conv_w + (size_t)gc * DC));
+    win[c][0] = bf16lo(wv.x); win[c][1] = bf16hi(wv.x); win[c][2] = bf16lo(wv.y); win[c][3] = bf16hi(wv.y);
+    cw[c][0] = bf16lo(cv.x); cw[c][1] = bf16hi(cv.x); cw[c][2] = bf16lo(cv.y); cw[c][3] = bf16hi(cv.y);
+    cb[c] = bf2f(L.conv_b[gc]);
+  }
+  float h[32];
+  bf16* sp = L.ssm_state + (((size_t)r * m.m_nheads + hh) * P + p) * N + quarter * 32;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(sp + j);
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { h[j + 2 * q] = bf16lo(w4[q]); h[j + 2 * q + 1] = bf16hi(w4[q]); }
+  }
+  const float A = -expf(bf2f(L.A_log[hh])), Dv = bf2f(L.Dp[hh]), dtb = bf2f(L.dt_bias[hh]);
+  const uint32_t* row = m.zxt + (size_t)r * m.ipo;
+  auto poll1 = [&](const uint32_t* q) {
+    uint32_t w = ld_relaxed_u32(q);
+    for (unsigned spins = 0; (w & 0xffffu) != tag_in; ++spins) {
+      if (spins > kMegaSpinLimit) asm volatile("trap;");
+      w = ld_relaxed_u32(q);
+    }
+    return untag(w);
+  };
+  for (int c = tid; c < CH; c += kMW * 32) {
+    const float xin = poll1(row + m.d_inner + chan(c));
+    float acc = cb[c];
+#pragma unroll
+    for (int j = 0; j < DC - 1; ++j) { win[c][j] = win[c][j + 1]; acc = fmaf(win[c][j], cw[c][j], acc); }
+    win[c][DC - 1] = xin;
+    acc = fmaf(xin, cw[c][DC - 1], acc);
+    cout[c] = rbf(acc / (1.0f + expf(-acc)));                 // SiLU, output in the activation dtype
+  }
+  const float dtr = poll1(row + m.d_inner + m.conv_dim + hh) + dtb;
+  if (stamp && tid == 0) *stamp = gtime();
+  asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
+  const float dt = dtr > 20.0f ? dtr : log1pf(expf(dtr));      // softplus (F.softplus threshold 20)
+  const float dA = expf(dt * A);
+  const float xp = cout[p], dtx = dt * xp;
+  float yacc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int n = quarter * 32 + j;
+    h[j] = fmaf(h[j], dA, dtx * cout[P + n]);
+    yacc = fmaf(h[j], cout[P + N + n], yacc);
+    h[j] = rbf(h[j]);                                          // decode: the stored state is in the cache dtype
+  }
+  yacc += __shfl_xor_sync(0xffffffffu, yacc, 1);
+  yacc += __shfl_xor_sync(0xffffffffu, yacc, 2);
+  if (quarter == 0) st_relaxed_u32(m.ygt + (size_t)r * m.d_inner + hh * P + p, tag_word(yacc + Dv * xp, tag_out));
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 v;
+    v.x = pack_bf16(h[j], h[j + 1]); v.y = pack_bf16(h[j + 2], h[j + 3]); v.z = pack_bf16(h[j + 4], h[j + 5]); v.w = pack_bf16(h[j + 6], h[j + 7]);
+    *reinterpret_cast<uint4*>(sp + j) = v;
+  }
+  for (int c = tid; c < CH; c += kMW * 32) {
+    if (c >= P && hh != 0) continue;                            // the shared B/C channels are written once (head 0)
+    uint2 o;
+    o.x = pack_bf16(win[c][0], win[c][1]); o.y = pack_bf16(win[c][2], win[c][3]);
+    *reinterpret_cast<uint2*>(L.conv_state + ((size_t)r * m.conv_dim + chan(c)) * DC) = o;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");   // scratch free for the next unit / phase
+}
+
 __device__ __forceinline__ void mega_fill(GemvArgs& a, const MegaArgs& m, int R) {
   memset(&a, 0, sizeof(a));
   a.M = R; a.eps = m.eps; a.norm_kind = m.norm_kind; a.T = 1; a.Hq = m.Hq; a.Hkv = m.Hkv; a.hd = m.hd;
@@ -1557,6 +1679,14 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     MegaLayer L = m.layers[0], Lnext = L;
     for (int li = 0; li < m.n_layer; ++li, L = Lnext) {
       if (li + 1 < m.n_layer) Lnext = m.layers[li + 1];       // the next layer's pointers are on their way while this one streams
+      if (L.kind == 1) {                                      // Mamba2 layer: in_proj [ipo, D], out_proj [D, d_inner]
+        mega_fill(a, m, R);
+        a.W = L.in_proj; a.N = m.ipo; a.K = m.D;
+        mega_produce<EPI_STORE>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+        a.W = L.out_proj; a.N = m.D; a.K = m.d_inner;
+        mega_produce<EPI_RESID>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+        continue;
+      }
       if (TC) {
         mega_produce_tc(L.in_t, m.tg[TG_QKV], m.D, ring, full_bar, empty_bar, S, gst, pol, lane);
         mega_produce_tc(L.out_t, m.tg[TG_OUT], qn, ring, full_bar, empty_bar, S, gst, pol, lane);
@@ -1586,7 +1716,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
 
   // ===== consumers =====
   const unsigned epoch = m.sync[1];                         // written by this session's previous live step
-  const int nph = 2 + m.n_layer * (4 + m.out_proj_repeats);
+  const int nph = m.nph;                                     // 2 + (4 + out_proj_repeats) per attention layer + 3 per Mamba2 layer
   int ph = 0, gst = 0, stamp_i = 0;
   const MegaAttnMeta ameta = mega_attention_meta(m, blockIdx.x, R * m.Hkv * m.nsplit);
   const bool stamping = m.timeline && blockIdx.x == 0;
@@ -1604,7 +1734,8 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   norm_prefetch(0, m.layers[0].norm_w, m.layers[0].norm_b);
-  norm_prefetch(1, m.layers[0].norm2_w, m.layers[0].norm2_b);
+  if (m.layers[0].kind == 1) norm_prefetch(1, m.layers[0].mnorm_w, m.layers[0].mnorm_w + m.D);
+  else norm_prefetch(1, m.layers[0].norm2_w, m.layers[0].norm2_b);
   MegaQkvPre qkv_pre; qkv_pre.valid = false; qkv_pre.pos = 0; qkv_pre.page = 0; qkv_pre.cs = make_float2(1.f, 0.f);
   {
     mega_fill(a, m, R);
@@ -1653,6 +1784,44 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
   MegaLayer L = m.layers[0], Lnext = L;
   for (int li = 0; li < m.n_layer; ++li, L = Lnext) {
     if (li + 1 < m.n_layer) Lnext = m.layers[li + 1];         // pointers of the next layer: loaded a layer before they are needed
+    // parameters of the next layer's two norm buffers: [0] its first norm (or the final norm), [1] norm2 of an attention
+    // layer or the 2 D = d_inner gated-norm weights of a Mamba2 layer
+    const bool lastl = li + 1 == m.n_layer;
+    const bf16* nx0w = lastl ? m.normf_w : Lnext.norm_w;
+    const bf16* nx0b = lastl ? m.normf_b : Lnext.norm_b;
+    const bf16* nx1w = Lnext.kind == 1 ? Lnext.mnorm_w : Lnext.norm2_w;
+    const bf16* nx1b = Lnext.kind == 1 ? Lnext.mnorm_w + m.D : Lnext.norm2_b;
+    if (!TC && L.kind == 1) {
+      // ---- Mamba2 layer: three phases instead of 4 + out_proj_repeats ----
+      // M1: norm -> in_proj -> z | xBC | dt as tagged words
+      mega_fill(a, m, R);
+      a.W = L.in_proj; a.N = m.ipo; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = L.norm_b ? nbuf + m.D : nullptr; a.ldy = m.ipo;
+      {
+        unsigned long long* slot = MEGA_STAMP_SLOT();
+        mega_consume<R, 2, 4, PRO_NORM, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.zxt, TAG(ph),
+                                                   nullptr, nullptr, nullptr, slot, 0);
+      }
+      MEGA_STAMP(); ++ph;
+      // M2: conv1d step + selective state update, one (row, head) unit per CTA
+      {
+        unsigned long long* slot = MEGA_STAMP_SLOT();
+        for (int unit = blockIdx.x; unit < R * m.m_nheads; unit += gridDim.x)
+          mega_scan_unit(m, L, unit, attn_scratch, TAG(ph - 1), TAG(ph), unit == (int)blockIdx.x ? slot : nullptr);
+      }
+      MEGA_STAMP(); ++ph;
+      norm_prefetch(0, nx0w, nx0b);                            // buffer 0 is free since M1
+      // M3: y * silu(z) -> gated RMSNorm -> out_proj + residual
+      mega_fill(a, m, R);
+      a.W = L.out_proj; a.N = m.D; a.K = m.d_inner; a.ldx = m.d_inner; a.ldy = m.D; a.ldr = m.D; a.nw = nbuf + 2 * m.D; a.nb = nullptr;
+      {
+        unsigned long long* slot = MEGA_STAMP_SLOT();
+        mega_consume<R, 2, 4, PRO_GATED, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ygt, TAG(ph - 1), m.xt, TAG(ph),
+                                                    m.xt, nullptr, nullptr, slot, 1, nullptr, nullptr, m.zxt, m.ipo, TAG(ph - 2));
+      }
+      MEGA_STAMP(); ++ph;
+      if (!lastl) norm_prefetch(1, nx1w, nx1b);                // buffer 1 is free since the gated norm
+      continue;
+    }
     // A: norm -> in_proj -> RoPE -> KV append (+ q)
     mega_fill(a, m, R);
     a.W = L.in_proj; a.N = nqkv; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = L.norm_b ? nbuf + m.D : nullptr; a.kv_layer = L.kv_layer;
@@ -1677,7 +1846,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     }
     MEGA_STAMP(); ++ph;
     // buffer 0 is free since the in_proj phase: the next layer's first norm (or the final norm) starts its way to shared memory
-    if (li + 1 < m.n_layer) norm_prefetch(0, Lnext.norm_w, Lnext.norm_b); else norm_prefetch(0, m.normf_w, m.normf_b);
+    norm_prefetch(0, nx0w, nx0b);
     // C/D: out_proj (twice in the reference); the slice stays in the ring between the passes
     {
       const int gst0 = gst;
@@ -1723,7 +1892,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
                                                 nullptr, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 220 : nullptr);
     }
     MEGA_STAMP(); ++ph;
-    if (li + 1 < m.n_layer) norm_prefetch(1, Lnext.norm2_w, Lnext.norm2_b);
+    if (!lastl) norm_prefetch(1, nx1w, nx1b);
     // F: fc2 + residual
     mega_fill(a, m, R);
     a.W = L.fc2; a.N = m.D; a.K = m.F; a.ldx = m.F; a.ldy = m.D; a.ldr = m.D;
@@ -2334,10 +2503,12 @@ static unsigned long long* g_steplog = nullptr;    // debug: set by zb_debug_ste
 
 // ---- persistent decode step (host side) ----
 size_t zb_mega_layers_bytes(const zb_model* model) { return (size_t)model->d.n_layer * sizeof(MegaLayer); }
+static int mega_ipo(const zb_model_desc& d) { return 2 * d.d_inner + 2 * d.m_ngroups * d.d_state + (d.m_headdim ? d.d_inner / d.m_headdim : 0); }
 size_t zb_mega_arena_bytes(const zb_model* model, int R) {
   const zb_model_desc& d = model->d;
   const size_t qn = (size_t)d.n_heads * d.head_dim, kn = (size_t)d.n_heads_kv * d.head_dim;
-  return ((size_t)R * (2 * d.d_model + 2 * qn + d.d_ff + 2 * kn)) * sizeof(uint32_t);
+  const size_t mamba = model->n_mamba > 0 ? (size_t)mega_ipo(d) + d.d_inner : 0;      // in_proj output row, y
+  return ((size_t)R * (2 * d.d_model + 2 * qn + d.d_ff + 2 * kn + mamba)) * sizeof(uint32_t);
 }
 
 bool zb_mega_tc_enabled(const zb_model* model, int R) {
@@ -2390,16 +2561,28 @@ static zb_status mega_tc_pretile(zb_ctx* ctx, const zb_model* model, const MegaT
 zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf, cudaStream_t stream) {
   const zb_model_desc& d = model->d;
   MegaTcPlan tp;
-  const bool tc = mega_tc_plan(d, ctx->num_sms, 2, &tp) && zb_mega_tc_enabled(model, 2) && d.heads;
+  const bool tc = model->n_mamba == 0 && mega_tc_plan(d, ctx->num_sms, 2, &tp) && zb_mega_tc_enabled(model, 2) && d.heads;
   if (tc) { if (zb_status st = mega_tc_pretile(ctx, model, tp, stream)) return st; }
   const size_t page_elems = (size_t)2 * d.n_heads_kv * ZB_PAGE_TOKENS * d.head_dim;
   MegaLayer* out = (MegaLayer*)host_buf;
   static const int share = env_int("ZB_DEBUG_SHARE_LAYERS", 0);   // debug: every layer streams layer 0's weights (L2-resident experiment)
   for (int li = 0; li < d.n_layer; ++li) {
     const zb_layer& L = model->layers[share ? 0 : li];
-    ZB_REQUIRE(ctx, L.kind == ZB_LAYER_ATTENTION, "persistent decode: layer %d is not an attention layer", li);
+    memset(&out[li], 0, sizeof(MegaLayer));
     out[li].norm_w = (const bf16*)L.norm_w; out[li].norm_b = (const bf16*)L.norm_b; out[li].in_proj = (const bf16*)L.in_proj;
-    out[li].out_proj = (const bf16*)L.out_proj; out[li].norm2_w = (const bf16*)L.norm2_w; out[li].norm2_b = (const bf16*)L.norm2_b;
+    out[li].out_proj = (const bf16*)L.out_proj;
+    if (L.kind == ZB_LAYER_MAMBA2) {
+      ZB_REQUIRE(ctx, cache->conv_state && cache->ssm_state, "persistent decode: Mamba2 layer %d but the cache has no conv/ssm state", li);
+      const int nheads = d.d_inner / d.m_headdim, conv_dim = d.d_inner + 2 * d.m_ngroups * d.d_state, mi = model->mamba_index[li];
+      out[li].kind = 1;
+      out[li].conv_w = (const bf16*)L.conv_w; out[li].conv_b = (const bf16*)L.conv_b; out[li].dt_bias = (const bf16*)L.dt_bias;
+      out[li].A_log = (const bf16*)L.A_log; out[li].Dp = (const bf16*)L.D; out[li].mnorm_w = (const bf16*)L.mnorm_w;
+      out[li].conv_state = (bf16*)cache->conv_state + (size_t)mi * cache->rows * conv_dim * d.d_conv;
+      out[li].ssm_state = (bf16*)cache->ssm_state + (size_t)mi * cache->rows * nheads * d.m_headdim * d.d_state;
+      continue;
+    }
+    ZB_REQUIRE(ctx, L.kind == ZB_LAYER_ATTENTION, "persistent decode: layer %d is neither an attention nor a Mamba2 layer", li);
+    out[li].norm2_w = (const bf16*)L.norm2_w; out[li].norm2_b = (const bf16*)L.norm2_b;
     out[li].fc1 = (const bf16*)L.fc1; out[li].fc2 = (const bf16*)L.fc2;
     out[li].kv_layer = (bf16*)cache->kv_pages + (size_t)model->attn_index[li] * cache->num_pages * page_elems;
     out[li].in_t = out[li].out_t = out[li].fc1_t = out[li].fc2_t = nullptr;
@@ -2417,7 +2600,13 @@ bool zb_mega_supported(const zb_model* model, int R) {
   static const int enabled = env_int("ZB_DECODE_MEGA", 1);
   auto k_ok = [](int K) { return K == 512 || K == 1024 || K == 2048 || K == 4096; };   // 512 k per warp, 8 warps
   const int qn = d.n_heads * d.head_dim;
-  if (model->n_mamba > 0) return false;                       // hybrid stacks use the multi-kernel graph path
+  if (model->n_mamba > 0) {
+    // hybrid stacks: Mamba2 layers as three phases of the same kernel (ZB_MEGA_HYBRID=0: the multi-kernel graph path)
+    const int grid = model->ctx->num_sms, ipo = mega_ipo(d);
+    if (!env_int("ZB_MEGA_HYBRID", 1) || d.m_headdim != 64 || d.d_state != 128 || d.d_conv != 4 || d.m_ngroups != 1 || d.d_inner != 2 * d.d_model ||
+        !k_ok(d.d_inner) || ((ipo + grid - 1) / grid) * R > kMW * 32)
+      return false;
+  }
   return enabled && R >= 2 && R <= 4 && d.head_dim == kHD && k_ok(d.d_model) && k_ok(qn) && (k_ok(d.d_ff) || d.d_ff == 8192) &&
          d.n_codebooks <= 16 && d.n_heads / d.n_heads_kv <= 8 && (d.out_proj_repeats == 1 || qn == d.d_model) &&
          d.out_proj_repeats >= 1 && d.out_proj_repeats <= 2 && (((d.n_heads + 2 * d.n_heads_kv) * d.head_dim) % 2 == 0);
@@ -2452,6 +2641,15 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     m.ht = p; p += (size_t)R * d.d_ff;
     m.kvt = p; p += (size_t)R * 2 * kn_;
   }
+  m.nph = 2;
+  for (int li = 0; li < d.n_layer; ++li) m.nph += model->layers[li].kind == ZB_LAYER_MAMBA2 ? 3 : 4 + d.out_proj_repeats;
+  if (model->n_mamba > 0) {
+    m.d_inner = d.d_inner; m.m_nheads = d.d_inner / d.m_headdim; m.ipo = mega_ipo(d); m.conv_dim = d.d_inner + 2 * d.m_ngroups * d.d_state;
+    const size_t qn_ = (size_t)d.n_heads * d.head_dim, kn_ = (size_t)d.n_heads_kv * d.head_dim;
+    uint32_t* p = arena + (size_t)R * (2 * d.d_model + 2 * qn_ + d.d_ff + 2 * kn_);
+    m.zxt = p; p += (size_t)R * m.ipo;
+    m.ygt = p;
+  }
   m.attn_part = s.part; m.attn_counters = ctx->counters; m.nsplit = nsplit;
   m.scale = 1.0f / sqrtf((float)d.head_dim); m.loop = loop; m.sync = sync; m.timeline = g_timeline; m.steplog = g_steplog;
   ZB_REQUIRE(ctx, cfg_scale != 1.0f, "persistent decode expects CFG rows");
@@ -2468,13 +2666,17 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
   pb = std::max(pb, part_need(d.d_ff, true, d.d_model, 2, 4));
   pb = std::max(pb, d.d_ff == 8192 ? part_need(d.d_model, false, d.d_ff, 4, 2) : part_need(d.d_model, false, d.d_ff, 2, 4));
   pb = std::max(pb, part_need(m.QV, false, d.d_model, 2, 4));
+  if (model->n_mamba > 0) {
+    pb = std::max(pb, part_need(m.ipo, false, d.d_model, 2, 4));
+    pb = std::max(pb, part_need(d.d_model, false, d.d_inner, 2, 4));
+  }
   pb = (pb + 1023) / 1024 * 1024;
   {  // one epilogue item per consumer thread
     const int max_items = std::max(((d.d_ff + grid - 1) / grid) * R, ((m.QV + grid - 1) / grid) * R);
     ZB_REQUIRE(ctx, max_items <= kMW * 32 && ((d.d_model + grid - 1) / grid) * R <= kMW * 32, "persistent decode: %d epilogue items per CTA", max_items);
   }
   MegaTcPlan tp;
-  const bool tc = zb_mega_tc_enabled(model, R) && mega_tc_plan(d, grid, R, &tp) && model->tcw && model->tcw_valid;
+  const bool tc = model->n_mamba == 0 && zb_mega_tc_enabled(model, R) && mega_tc_plan(d, grid, R, &tp) && model->tcw && model->tcw_valid;
   if (tc) {
     for (int k = 0; k < TG_COUNT; ++k) m.tg[k] = tp.g[k];
     m.heads_t = (const bf16*)((const char*)model->tcw + tp.off[TG_HEADS]);

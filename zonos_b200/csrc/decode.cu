@@ -873,10 +873,11 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
     if (spins > kMegaSpinLimit) asm volatile("trap;");
   }
   if (PRO == PRO_GATED) {
-    // mamba_ssm RMSNormGated (norm_before_gate = False): g = y * silu(z) in fp32 from the bf16 y (this phase's input) and the
-    // bf16 z columns of the in_proj output (tagged by that earlier phase), xn = bf16(g * rsqrt(mean(g^2) + 1e-5) * w)
+    // mamba_ssm RMSNormGated (norm_before_gate = False): g = y * silu(z) stays fp32 up to xn = bf16(g * rsqrt(mean(g^2) + 1e-5) * w).
+    // The scan phase publishes g as two tagged 16-bit halves (xt: high halves, already in xf; zt: low halves).
     for (unsigned spins = 0;; ++spins) {
       bool ok = true;
+      uint32_t lo[R][NC * 8];
 #pragma unroll
       for (int i = 0; i < R; ++i)
 #pragma unroll
@@ -884,23 +885,17 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
           const uint32_t* src = zt + (size_t)i * ldz + koff + c * 256 + lane * 8;
           const uint4 v0 = ld_relaxed_v4(src), v1 = ld_relaxed_v4(src + 4);
           ok = ok && tags_ok(v0, tag_z) && tags_ok(v1, tag_z);
-          const float zz[8] = {untag(v0.x), untag(v0.y), untag(v0.z), untag(v0.w), untag(v1.x), untag(v1.y), untag(v1.z), untag(v1.w)};
-          if (ok) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) xf[i][c * 8 + e] = xf[i][c * 8 + e] * (zz[e] / (1.0f + expf(-zz[e])));
-          }
+          lo[i][c * 8 + 0] = v0.x; lo[i][c * 8 + 1] = v0.y; lo[i][c * 8 + 2] = v0.z; lo[i][c * 8 + 3] = v0.w;
+          lo[i][c * 8 + 4] = v1.x; lo[i][c * 8 + 5] = v1.y; lo[i][c * 8 + 6] = v1.z; lo[i][c * 8 + 7] = v1.w;
         }
-      if (ok) break;                                            // (a failed round leaves some xf scaled: reload them)
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+          for (int e = 0; e < NC * 8; ++e) xf[i][e] = __uint_as_float(__float_as_uint(xf[i][e]) | (lo[i][e] >> 16));
+        break;
+      }
       if (spins > kMegaSpinLimit) asm volatile("trap;");
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const uint32_t* src = xt + (size_t)i * a.ldx + koff + c * 256 + lane * 8;
-          const uint4 v0 = ld_relaxed_v4(src), v1 = ld_relaxed_v4(src + 4);
-          xf[i][c * 8 + 0] = untag(v0.x); xf[i][c * 8 + 1] = untag(v0.y); xf[i][c * 8 + 2] = untag(v0.z); xf[i][c * 8 + 3] = untag(v0.w);
-          xf[i][c * 8 + 4] = untag(v1.x); xf[i][c * 8 + 5] = untag(v1.y); xf[i][c * 8 + 6] = untag(v1.z); xf[i][c * 8 + 7] = untag(v1.w);
-        }
     }
   }
   if (stamp && threadIdx.x == 0) *stamp = gtime();
@@ -1554,8 +1549,27 @@ __device__ __forceinline__ void mega_attention_unit(const MegaArgs& m, const bf1
 // selective_state_update, reached from zonos/backbone/_mamba_ssm.py:45-58).  Inputs: tagged words of the in_proj output
 // row (z | xBC | dt); output: y as tagged bf16 words - the gate y * silu(z) is applied by the out_proj prologue (PRO_GATED),
 // which keeps the product in fp32 like RMSNormGated does.
+constexpr int kScanStageOff = 16 * 1024;                      // staging area of the prefetched state inside the phase scratch
+// recurrent state of this CTA's first unit: cp.async into shared memory before the in_proj phase (it depends on earlier steps
+// only), so the scan phase does not start with an HBM round trip.  Thread t stages exactly what thread t consumes.
+__device__ __forceinline__ void mega_scan_prefetch(const MegaArgs& m, const MegaLayer& L, int unit, unsigned char* scratch) {
+  constexpr int P = 64, N = 128, DC = 4, CH = P + 2 * N;
+  if (unit < 0) { asm volatile("cp.async.commit_group;" ::: "memory"); return; }
+  const int tid = threadIdx.x, r = unit / m.m_nheads, hh = unit % m.m_nheads;
+  const int p = tid >> 2, quarter = tid & 3;
+  unsigned char* st = scratch + kScanStageOff;
+  const bf16* sp = L.ssm_state + (((size_t)r * m.m_nheads + hh) * P + p) * N + quarter * 32;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cp_async16(st + tid * 64 + j * 16, sp + j * 8);
+  for (int c = tid; c < CH; c += kMW * 32) {
+    const int gc = c < P ? hh * P + c : m.d_inner + (c - P);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(st + 16384 + c * 8)), "l"(L.conv_state + ((size_t)r * m.conv_dim + gc) * DC) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLayer& L, int unit, unsigned char* scratch, uint32_t tag_in, uint32_t tag_out,
-                                               unsigned long long* stamp) {
+                                               unsigned long long* stamp, bool prefetched) {
   constexpr int P = 64, N = 128, DC = 4, CH = P + 2 * N;
   float (*win)[DC] = reinterpret_cast<float (*)[DC]>(scratch);                 // [CH][DC] rolling window, oldest first
   float (*cw)[DC] = reinterpret_cast<float (*)[DC]>(scratch + CH * DC * 4);
@@ -1564,10 +1578,13 @@ __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLaye
   const int tid = threadIdx.x, r = unit / m.m_nheads, hh = unit % m.m_nheads;
   const int p = tid >> 2, quarter = tid & 3;
   auto chan = [&](int c) { return c < P ? hh * P + c : m.d_inner + (c - P); };   // index into xBC / conv_state
-  // state of earlier steps: does not depend on this step's activations, so it is fetched before the inputs are polled
+  // state of earlier steps: staged by mega_scan_prefetch, or fetched now
+  const unsigned char* st = scratch + kScanStageOff;
+  if (prefetched) asm volatile("cp.async.wait_group 0;" ::: "memory");
   for (int c = tid; c < CH; c += kMW * 32) {
     const int gc = chan(c);
-    const uint2 wv = *reinterpret_cast<const uint2*>(L.conv_state + ((size_t)r * m.conv_dim + gc) * DC);
+    const uint2 wv = prefetched ? *reinterpret_cast<const uint2*>(st + 16384 + c * 8)
+                                : *reinterpret_cast<const uint2*>(L.conv_state + ((size_t)r * m.conv_dim + gc) * DC);
     const uint2 cv = __ldg(reinterpret_cast<const uint2*>(L.conv_w + (size_t)gc * DC));
     win[c][0] = bf16lo(wv.x); win[c][1] = bf16hi(wv.x); win[c][2] = bf16lo(wv.y); win[c][3] = bf16hi(wv.y);
     cw[c][0] = bf16lo(cv.x); cw[c][1] = bf16hi(cv.x); cw[c][2] = bf16lo(cv.y); cw[c][3] = bf16hi(cv.y);
@@ -1577,7 +1594,7 @@ __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLaye
   bf16* sp = L.ssm_state + (((size_t)r * m.m_nheads + hh) * P + p) * N + quarter * 32;
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
-    const uint4 v = *reinterpret_cast<const uint4*>(sp + j);
+    const uint4 v = prefetched ? *reinterpret_cast<const uint4*>(st + tid * 64 + j * 2) : *reinterpret_cast<const uint4*>(sp + j);
     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) { h[j + 2 * q] = bf16lo(w4[q]); h[j + 2 * q + 1] = bf16hi(w4[q]); }
@@ -1602,6 +1619,7 @@ __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLaye
     cout[c] = rbf(acc / (1.0f + expf(-acc)));                 // SiLU, output in the activation dtype
   }
   const float dtr = poll1(row + m.d_inner + m.conv_dim + hh) + dtb;
+  const float zg = quarter == 0 ? poll1(row + hh * P + p) : 0.f;   // gate input of this thread's output element
   if (stamp && tid == 0) *stamp = gtime();
   asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
   const float dt = dtr > 20.0f ? dtr : log1pf(expf(dtr));      // softplus (F.softplus threshold 20)
@@ -1617,7 +1635,14 @@ __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLaye
   }
   yacc += __shfl_xor_sync(0xffffffffu, yacc, 1);
   yacc += __shfl_xor_sync(0xffffffffu, yacc, 2);
-  if (quarter == 0) st_relaxed_u32(m.ygt + (size_t)r * m.d_inner + hh * P + p, tag_word(yacc + Dv * xp, tag_out));
+  if (quarter == 0) {
+    // g = bf16(y) * silu(z) in fp32 (what RMSNormGated computes from the bf16 y and z), published as two tagged 16-bit halves
+    const float y = rbf(yacc + Dv * xp);
+    const uint32_t gb = __float_as_uint(y * (zg / (1.0f + expf(-zg))));
+    uint32_t* dst = m.ygt + (size_t)r * 2 * m.d_inner + hh * P + p;
+    st_relaxed_u32(dst, (gb & 0xffff0000u) | tag_out);
+    st_relaxed_u32(dst + m.d_inner, (gb << 16) | tag_out);
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     uint4 v;
@@ -1796,27 +1821,29 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       // M1: norm -> in_proj -> z | xBC | dt as tagged words
       mega_fill(a, m, R);
       a.W = L.in_proj; a.N = m.ipo; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = L.norm_b ? nbuf + m.D : nullptr; a.ldy = m.ipo;
+      const bool has_unit = (int)blockIdx.x < R * m.m_nheads;
+      mega_scan_prefetch(m, L, has_unit ? (int)blockIdx.x : -1, attn_scratch);
       {
         unsigned long long* slot = MEGA_STAMP_SLOT();
         mega_consume<R, 2, 4, PRO_NORM, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.zxt, TAG(ph),
-                                                   nullptr, nullptr, nullptr, slot, 0);
+                                                   nullptr, nullptr, nullptr, slot, 1);
       }
       MEGA_STAMP(); ++ph;
       // M2: conv1d step + selective state update, one (row, head) unit per CTA
       {
         unsigned long long* slot = MEGA_STAMP_SLOT();
         for (int unit = blockIdx.x; unit < R * m.m_nheads; unit += gridDim.x)
-          mega_scan_unit(m, L, unit, attn_scratch, TAG(ph - 1), TAG(ph), unit == (int)blockIdx.x ? slot : nullptr);
+          mega_scan_unit(m, L, unit, attn_scratch, TAG(ph - 1), TAG(ph), unit == (int)blockIdx.x ? slot : nullptr, unit == (int)blockIdx.x);
       }
       MEGA_STAMP(); ++ph;
       norm_prefetch(0, nx0w, nx0b);                            // buffer 0 is free since M1
       // M3: y * silu(z) -> gated RMSNorm -> out_proj + residual
       mega_fill(a, m, R);
-      a.W = L.out_proj; a.N = m.D; a.K = m.d_inner; a.ldx = m.d_inner; a.ldy = m.D; a.ldr = m.D; a.nw = nbuf + 2 * m.D; a.nb = nullptr;
+      a.W = L.out_proj; a.N = m.D; a.K = m.d_inner; a.ldx = 2 * m.d_inner; a.ldy = m.D; a.ldr = m.D; a.nw = nbuf + 2 * m.D; a.nb = nullptr;
       {
         unsigned long long* slot = MEGA_STAMP_SLOT();
         mega_consume<R, 2, 4, PRO_GATED, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ygt, TAG(ph - 1), m.xt, TAG(ph),
-                                                    m.xt, nullptr, nullptr, slot, 1, nullptr, nullptr, m.zxt, m.ipo, TAG(ph - 2));
+                                                    m.xt, nullptr, nullptr, slot, 1, nullptr, nullptr, m.ygt + m.d_inner, 2 * m.d_inner, TAG(ph - 1));
       }
       MEGA_STAMP(); ++ph;
       if (!lastl) norm_prefetch(1, nx1w, nx1b);                // buffer 1 is free since the gated norm
@@ -2507,7 +2534,7 @@ static int mega_ipo(const zb_model_desc& d) { return 2 * d.d_inner + 2 * d.m_ngr
 size_t zb_mega_arena_bytes(const zb_model* model, int R) {
   const zb_model_desc& d = model->d;
   const size_t qn = (size_t)d.n_heads * d.head_dim, kn = (size_t)d.n_heads_kv * d.head_dim;
-  const size_t mamba = model->n_mamba > 0 ? (size_t)mega_ipo(d) + d.d_inner : 0;      // in_proj output row, y
+  const size_t mamba = model->n_mamba > 0 ? (size_t)mega_ipo(d) + 2 * d.d_inner : 0;  // in_proj output row, g (two 16-bit halves)
   return ((size_t)R * (2 * d.d_model + 2 * qn + d.d_ff + 2 * kn + mamba)) * sizeof(uint32_t);
 }
 

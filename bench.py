@@ -352,7 +352,11 @@ def run_b200(args):
             tpath = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tpath) and not spec["hybrid"] and not P:
                 traffic = json.load(open(tpath)).get("batch%d_decode_step_dram_bytes_per_launch" % B)
-            if spec["hybrid"]:
+            if spec["hybrid"] and 2 * B <= 4:
+                kname = "decode_step_kernel<R=%d> (persistent FFMA2 consumer, hybrid stack: Mamba2 layers as three tagged-word phases - in_proj, conv1d " \
+                        "step + selective state update, gated norm + out_proj - next to the attention layers; embed + %d layers + heads, one launch " \
+                        "per frame) + sample kernel" % (2 * B, spec["n_layer"])
+            elif spec["hybrid"]:
                 kname = "decode step of the hybrid stack as ONE CUDA graph of %d layers (gemv3_kernel / gemm_tc_kernel Linears, mamba_scan_kernel, " \
                         "gated_norm_kernel, attn_kernel) + sample kernel, R=%d rows" % (spec["n_layer"], 2 * B)
             elif 2 * B <= 4:

@@ -1123,7 +1123,7 @@ __device__ __forceinline__ void mega_consume_tc(const GemvArgs& a, const MegaTcG
 #define DBG(i) do { if (dbg && threadIdx.x == 0) dbg[i] = gtime(); } while (0)
   const int tid = threadIdx.x;                                // consumer threads 0 .. 255
   if ((int)blockIdx.x >= g.nunits) return;                    // no unit of this matrix (the producer skipped it alike)
-  const int K = a.K, nchunk8 = K / 8, nkb = K / 64;
+  const int K = a.K, nchunk8 = K / 8;
   // activations: thread t holds elements [8 q, 8 q + 8) of every row for q = t + 256 c; spin on the operand loads
   // themselves until every word carries the producing phase's tag
   float xf[R][NR * 8];
@@ -2053,10 +2053,22 @@ __global__ void __launch_bounds__(256) mamba_scan_kernel(ScanArgs a) {
   }
   const float A = -expf(bf2f(a.A_log[hh])), Dv = bf2f(a.Dp[hh]), dtb = bf2f(a.dt_bias[hh]);
   __syncthreads();
+  // the token loop is a chain of dependent steps: the next token's inputs (this thread's conv channels, dt, z) are loaded
+  // while the current one is processed - two exposed L2 round trips per token otherwise
+  const int c0 = tid, c1 = tid + 256;                            // this thread's conv channels (c1 only for tid < CH - 256)
+  const bf16* row0 = a.zx + (size_t)r * a.T * a.in_proj_out;
+  float nx0 = bf2f(row0[a.d_inner + chan(c0)]), nx1 = c1 < CH ? bf2f(row0[a.d_inner + chan(c1)]) : 0.f;
+  float ndt = bf2f(row0[a.d_inner + a.conv_dim + hh]), nz = bf2f(row0[hh * P + p]);
   for (int t = 0; t < a.T; ++t) {
-    const bf16* row = a.zx + ((size_t)r * a.T + t) * a.in_proj_out;
+    const float x0 = nx0, x1 = nx1, dt_in = ndt, z_in = nz;
+    if (t + 1 < a.T) {
+      const bf16* nrow = a.zx + ((size_t)r * a.T + t + 1) * a.in_proj_out;
+      nx0 = bf2f(nrow[a.d_inner + chan(c0)]);
+      if (c1 < CH) nx1 = bf2f(nrow[a.d_inner + chan(c1)]);
+      ndt = bf2f(nrow[a.d_inner + a.conv_dim + hh]); nz = bf2f(nrow[hh * P + p]);
+    }
     for (int c = tid; c < CH; c += 256) {
-      const float xin = bf2f(row[a.d_inner + chan(c)]);
+      const float xin = c == c0 ? x0 : x1;
       float acc = cb[c];
 #pragma unroll
       for (int j = 0; j < DC - 1; ++j) { win[c][j] = win[c][j + 1]; acc = fmaf(win[c][j], cw[c][j], acc); }
@@ -2065,7 +2077,7 @@ __global__ void __launch_bounds__(256) mamba_scan_kernel(ScanArgs a) {
       cout[c] = rbf(acc / (1.0f + expf(-acc)));               // SiLU, output in the activation dtype
     }
     __syncthreads();
-    const float dtr = bf2f(row[a.d_inner + a.conv_dim + hh]) + dtb;
+    const float dtr = dt_in + dtb;
     const float dt = dtr > 20.0f ? dtr : log1pf(expf(dtr));      // softplus (F.softplus threshold 20)
     const float dA = expf(dt * A);
     const float xp = cout[p], dtx = dt * xp;
@@ -2081,7 +2093,7 @@ __global__ void __launch_bounds__(256) mamba_scan_kernel(ScanArgs a) {
     yacc += __shfl_xor_sync(0xffffffffu, yacc, 2);
     if (quarter == 0) {
       const float y = rbf(yacc + Dv * xp);
-      const float z = bf2f(row[hh * P + p]);
+      const float z = z_in;
       a.g[((size_t)r * a.T + t) * a.d_inner + hh * P + p] = y * (z / (1.0f + expf(-z)));
     }
     __syncthreads();

@@ -350,8 +350,8 @@ def run_b200(args):
             achieved = step_bytes / (step_ms * 1e-3) / 1e9
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tpath) and not spec["hybrid"] and not P:
-                traffic = json.load(open(tpath)).get("batch%d_decode_step_dram_bytes_per_launch" % B)
+            if os.path.exists(tpath) and not P:
+                traffic = json.load(open(tpath)).get(("hybrid_" if spec["hybrid"] else "") + "batch%d_decode_step_dram_bytes_per_launch" % B)
             if spec["hybrid"] and 2 * B <= 4:
                 kname = "decode_step_kernel<R=%d> (persistent FFMA2 consumer, hybrid stack: Mamba2 layers as three tagged-word phases - in_proj, conv1d " \
                         "step + selective state update, gated norm + out_proj - next to the attention layers; embed + %d layers + heads, one launch " \

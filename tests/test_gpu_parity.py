@@ -452,6 +452,32 @@ def test_hybrid_generate_matches_oracle():
         assert torch.equal(codes.cpu(), ref)
 
 
+@pytest.mark.parametrize("B", [1, 2])
+def test_hybrid_generate_persistent_kernel_and_graph_path(B, monkeypatch):
+    """Hybrid decode takes the persistent kernel for B <= 2 (Mamba2 layers as three tagged-word phases: in_proj, conv1d step +
+    state update, gated norm + out_proj); `ZB_MEGA_HYBRID=0` forces the multi-kernel CUDA graph.  Both against the oracle
+    step by step (logits within tolerance while the histories agree, tokens unless a float near-tie), and the recurrent
+    state they leave behind must agree with each other."""
+    model, oracle, _ = _hybrid_model(DEV)
+    Lc, N = 9, 16
+    cond = make_conditioning(2 * B, Lc, 512, seed=12)
+    q = q_stream_from_seed(6, N + 9, B)
+    otrace = {}
+    ref = o_gen.generate(oracle, cond, None, N, 2.0, B, dict(min_p=0.1), q_stream=q, trace=otrace)
+    launches = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("ZB_MEGA_HYBRID", mode)
+        trace = {}
+        l0 = model._ctx().launch_count()
+        codes = model.generate(cond.to(DEV), max_new_tokens=N, batch_size=B, q_stream=q, trace=trace)
+        launches[mode] = model._ctx().launch_count() - l0
+        same = [check_generate_against_oracle(_sub_trace(trace, [b]), _sub_trace(otrace, [b]), dict(min_p=0.1), q[:, [b]], 0) for b in range(B)]
+        for b in range(B):
+            if same[b]:
+                assert torch.equal(codes[b].cpu(), ref[b])
+    assert launches["1"] > 0 and launches["0"] > 0
+
+
 def test_hybrid_rms_norm_checkpoint_layout():
     """A hybrid checkpoint trained with rms_norm=true has weight-only norms (mamba_ssm RMSNorm): the state dict must load
     without `.bias` keys and the kernels must take the RMS path (zonos/backbone/_mamba_ssm.py:18-40)."""

@@ -1558,9 +1558,9 @@ __device__ __forceinline__ void mega_scan_prefetch(const MegaArgs& m, const Mega
   const int tid = threadIdx.x, r = unit / m.m_nheads, hh = unit % m.m_nheads;
   const int p = tid >> 2, quarter = tid & 3;
   unsigned char* st = scratch + kScanStageOff;
-  const bf16* sp = L.ssm_state + (((size_t)r * m.m_nheads + hh) * P + p) * N + quarter * 32;
+  const bf16* sp = L.ssm_state + (((size_t)r * m.m_nheads + hh) * P + p) * N + quarter * 8;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) cp_async16(st + tid * 64 + j * 16, sp + j * 8);
+  for (int j = 0; j < 4; ++j) cp_async16(st + tid * 64 + j * 16, sp + j * 32);
   for (int c = tid; c < CH; c += kMW * 32) {
     const int gc = c < P ? hh * P + c : m.d_inner + (c - P);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(st + 16384 + c * 8)), "l"(L.conv_state + ((size_t)r * m.conv_dim + gc) * DC) : "memory");
@@ -1571,8 +1571,8 @@ __device__ __forceinline__ void mega_scan_prefetch(const MegaArgs& m, const Mega
 __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLayer& L, int unit, unsigned char* scratch, uint32_t tag_in, uint32_t tag_out,
                                                unsigned long long* stamp, bool prefetched) {
   constexpr int P = 64, N = 128, DC = 4, CH = P + 2 * N;
-  float (*win)[DC] = reinterpret_cast<float (*)[DC]>(scratch);                 // [CH][DC] rolling window, oldest first
-  float (*cw)[DC] = reinterpret_cast<float (*)[DC]>(scratch + CH * DC * 4);
+  float (*win)[CH] = reinterpret_cast<float (*)[CH]>(scratch);                 // [DC][CH] rolling window, oldest first (channel-contiguous)
+  float (*cw)[CH] = reinterpret_cast<float (*)[CH]>(scratch + CH * DC * 4);
   float* cb = reinterpret_cast<float*>(scratch + 2 * CH * DC * 4);
   float* cout = cb + CH;
   const int tid = threadIdx.x, r = unit / m.m_nheads, hh = unit % m.m_nheads;
@@ -1586,15 +1586,16 @@ __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLaye
     const uint2 wv = prefetched ? *reinterpret_cast<const uint2*>(st + 16384 + c * 8)
                                 : *reinterpret_cast<const uint2*>(L.conv_state + ((size_t)r * m.conv_dim + gc) * DC);
     const uint2 cv = __ldg(reinterpret_cast<const uint2*>(L.conv_w + (size_t)gc * DC));
-    win[c][0] = bf16lo(wv.x); win[c][1] = bf16hi(wv.x); win[c][2] = bf16lo(wv.y); win[c][3] = bf16hi(wv.y);
-    cw[c][0] = bf16lo(cv.x); cw[c][1] = bf16hi(cv.x); cw[c][2] = bf16lo(cv.y); cw[c][3] = bf16hi(cv.y);
+    win[0][c] = bf16lo(wv.x); win[1][c] = bf16hi(wv.x); win[2][c] = bf16lo(wv.y); win[3][c] = bf16hi(wv.y);
+    cw[0][c] = bf16lo(cv.x); cw[1][c] = bf16hi(cv.x); cw[2][c] = bf16lo(cv.y); cw[3][c] = bf16hi(cv.y);
     cb[c] = bf2f(L.conv_b[gc]);
   }
   float h[32];
-  bf16* sp = L.ssm_state + (((size_t)r * m.m_nheads + hh) * P + p) * N + quarter * 32;
+  // state elements of this thread: n = 32 k + 8 quarter + e (see mamba_scan_kernel)
+  bf16* sp = L.ssm_state + (((size_t)r * m.m_nheads + hh) * P + p) * N + quarter * 8;
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
-    const uint4 v = prefetched ? *reinterpret_cast<const uint4*>(st + tid * 64 + j * 2) : *reinterpret_cast<const uint4*>(sp + j);
+    const uint4 v = prefetched ? *reinterpret_cast<const uint4*>(st + tid * 64 + j * 2) : *reinterpret_cast<const uint4*>(sp + 4 * j);
     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) { h[j + 2 * q] = bf16lo(w4[q]); h[j + 2 * q + 1] = bf16hi(w4[q]); }
@@ -1613,9 +1614,9 @@ __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLaye
     const float xin = poll1(row + m.d_inner + chan(c));
     float acc = cb[c];
 #pragma unroll
-    for (int j = 0; j < DC - 1; ++j) { win[c][j] = win[c][j + 1]; acc = fmaf(win[c][j], cw[c][j], acc); }
-    win[c][DC - 1] = xin;
-    acc = fmaf(xin, cw[c][DC - 1], acc);
+    for (int j = 0; j < DC - 1; ++j) { win[j][c] = win[j + 1][c]; acc = fmaf(win[j][c], cw[j][c], acc); }
+    win[DC - 1][c] = xin;
+    acc = fmaf(xin, cw[DC - 1][c], acc);
     cout[c] = rbf(acc / (1.0f + expf(-acc)));                 // SiLU, output in the activation dtype
   }
   const float dtr = poll1(row + m.d_inner + m.conv_dim + hh) + dtb;
@@ -1628,7 +1629,7 @@ __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLaye
   float yacc = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const int n = quarter * 32 + j;
+    const int n = (j >> 3) * 32 + quarter * 8 + (j & 7);
     h[j] = fmaf(h[j], dA, dtx * cout[P + n]);
     yacc = fmaf(h[j], cout[P + N + n], yacc);
     h[j] = rbf(h[j]);                                          // decode: the stored state is in the cache dtype
@@ -1647,12 +1648,12 @@ __device__ __forceinline__ void mega_scan_unit(const MegaArgs& m, const MegaLaye
   for (int j = 0; j < 32; j += 8) {
     uint4 v;
     v.x = pack_bf16(h[j], h[j + 1]); v.y = pack_bf16(h[j + 2], h[j + 3]); v.z = pack_bf16(h[j + 4], h[j + 5]); v.w = pack_bf16(h[j + 6], h[j + 7]);
-    *reinterpret_cast<uint4*>(sp + j) = v;
+    *reinterpret_cast<uint4*>(sp + 4 * j) = v;
   }
   for (int c = tid; c < CH; c += kMW * 32) {
     if (c >= P && hh != 0) continue;                            // the shared B/C channels are written once (head 0)
     uint2 o;
-    o.x = pack_bf16(win[c][0], win[c][1]); o.y = pack_bf16(win[c][2], win[c][3]);
+    o.x = pack_bf16(win[0][c], win[1][c]); o.y = pack_bf16(win[2][c], win[3][c]);
     *reinterpret_cast<uint2*>(L.conv_state + ((size_t)r * m.conv_dim + chan(c)) * DC) = o;
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");   // scratch free for the next unit / phase
@@ -2019,46 +2020,55 @@ struct ScanArgs {
   const zb_loop_state* loop; int T_delayed;
 };
 
-__global__ void __launch_bounds__(256) mamba_scan_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(256, 4) mamba_scan_kernel(ScanArgs a) {
   pdl_launch_dependents();
   pdl_wait();
   if (loop_idle(a.loop, a.T_delayed)) return;
   constexpr int P = 64, N = 128, DC = 4;                       // headdim, d_state, d_conv (checked on the host)
   constexpr int CH = P + 2 * N;                                // channels this CTA convolves: its 64 x + B + C
-  __shared__ float win[CH][DC];                                // rolling window, oldest first
-  __shared__ float cw[CH][DC];
+  __shared__ float win[DC][CH];                                // rolling window, oldest first; channel-contiguous: no bank conflicts
+  __shared__ float cw[DC][CH];
   __shared__ float cb[CH];
   __shared__ float cout[CH];
   const int r = blockIdx.x, hh = blockIdx.y, tid = threadIdx.x;
   const int p = tid >> 2, quarter = tid & 3;
   auto chan = [&](int c) { return c < P ? hh * P + c : a.d_inner + (c - P); };   // index into xBC / conv_state
-  for (int c = tid; c < CH; c += 256) {
-    const int gc = chan(c);
-    for (int j = 0; j < DC; ++j) {
-      win[c][j] = bf2f(a.conv_state[((size_t)r * a.conv_dim + gc) * DC + j]);
-      cw[c][j] = bf2f(a.conv_w[(size_t)gc * DC + j]);
-    }
-    cb[c] = bf2f(a.conv_b[gc]);
+  // A CTA is one short chain load -> conv -> state update -> store, and only 4 fit an SM (h[32] per thread): issue EVERY
+  // independent load before the first use, 8 / 16 bytes at a time (decode at 64 rows was 78 us per launch against 21 us of bytes)
+  const int c0 = tid, c1 = tid + 256;                            // this thread's conv channels (c1 only for tid < CH - 256)
+  const bool has1 = c1 < CH;
+  const int g0 = chan(c0), g1 = has1 ? chan(c1) : g0;
+  // state elements of this thread: n = 32 k + 8 quarter + e (k < 4, e < 8): the four threads of a state row read 64 contiguous
+  // bytes per load, and their shared-memory reads of B / C below fall into different banks
+  bf16* sp = a.ssm_state + (((size_t)r * a.nheads + hh) * P + p) * N + quarter * 8;
+  uint4 sv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sv[j] = *reinterpret_cast<const uint4*>(sp + 32 * j);
+  const uint2 ws0 = *reinterpret_cast<const uint2*>(a.conv_state + ((size_t)r * a.conv_dim + g0) * DC);
+  const uint2 ws1 = has1 ? *reinterpret_cast<const uint2*>(a.conv_state + ((size_t)r * a.conv_dim + g1) * DC) : make_uint2(0, 0);
+  const uint2 wc0 = __ldg(reinterpret_cast<const uint2*>(a.conv_w + (size_t)g0 * DC));
+  const uint2 wc1 = __ldg(reinterpret_cast<const uint2*>(a.conv_w + (size_t)g1 * DC));
+  const float b0 = bf2f(a.conv_b[g0]), b1 = bf2f(a.conv_b[g1]);
+  const bf16* row0 = a.zx + (size_t)r * a.T * a.in_proj_out;
+  float nx0 = bf2f(row0[a.d_inner + g0]), nx1 = has1 ? bf2f(row0[a.d_inner + g1]) : 0.f;
+  float ndt = bf2f(row0[a.d_inner + a.conv_dim + hh]), nz = bf2f(row0[hh * P + p]);
+  const float A = -expf(bf2f(a.A_log[hh])), Dv = bf2f(a.Dp[hh]), dtb = bf2f(a.dt_bias[hh]);
+  win[0][c0] = bf16lo(ws0.x); win[1][c0] = bf16hi(ws0.x); win[2][c0] = bf16lo(ws0.y); win[3][c0] = bf16hi(ws0.y);
+  cw[0][c0] = bf16lo(wc0.x); cw[1][c0] = bf16hi(wc0.x); cw[2][c0] = bf16lo(wc0.y); cw[3][c0] = bf16hi(wc0.y);
+  cb[c0] = b0;
+  if (has1) {
+    win[0][c1] = bf16lo(ws1.x); win[1][c1] = bf16hi(ws1.x); win[2][c1] = bf16lo(ws1.y); win[3][c1] = bf16hi(ws1.y);
+    cw[0][c1] = bf16lo(wc1.x); cw[1][c1] = bf16hi(wc1.x); cw[2][c1] = bf16lo(wc1.y); cw[3][c1] = bf16hi(wc1.y);
+    cb[c1] = b1;
   }
   float h[32];
-  {
-    const bf16* sp = a.ssm_state + (((size_t)r * a.nheads + hh) * P + p) * N + quarter * 32;
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(sp + j);
-      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w4[4] = {sv[j].x, sv[j].y, sv[j].z, sv[j].w};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { h[j + 2 * q] = bf16lo(w4[q]); h[j + 2 * q + 1] = bf16hi(w4[q]); }
-    }
+    for (int q = 0; q < 4; ++q) { h[8 * j + 2 * q] = bf16lo(w4[q]); h[8 * j + 2 * q + 1] = bf16hi(w4[q]); }
   }
-  const float A = -expf(bf2f(a.A_log[hh])), Dv = bf2f(a.Dp[hh]), dtb = bf2f(a.dt_bias[hh]);
-  __syncthreads();
-  // the token loop is a chain of dependent steps: the next token's inputs (this thread's conv channels, dt, z) are loaded
-  // while the current one is processed - two exposed L2 round trips per token otherwise
-  const int c0 = tid, c1 = tid + 256;                            // this thread's conv channels (c1 only for tid < CH - 256)
-  const bf16* row0 = a.zx + (size_t)r * a.T * a.in_proj_out;
-  float nx0 = bf2f(row0[a.d_inner + chan(c0)]), nx1 = c1 < CH ? bf2f(row0[a.d_inner + chan(c1)]) : 0.f;
-  float ndt = bf2f(row0[a.d_inner + a.conv_dim + hh]), nz = bf2f(row0[hh * P + p]);
+  // (each thread reads back only the window / weights of its own channels: no barrier needed before the token loop)
   for (int t = 0; t < a.T; ++t) {
     const float x0 = nx0, x1 = nx1, dt_in = ndt, z_in = nz;
     if (t + 1 < a.T) {
@@ -2071,9 +2081,9 @@ __global__ void __launch_bounds__(256) mamba_scan_kernel(ScanArgs a) {
       const float xin = c == c0 ? x0 : x1;
       float acc = cb[c];
 #pragma unroll
-      for (int j = 0; j < DC - 1; ++j) { win[c][j] = win[c][j + 1]; acc = fmaf(win[c][j], cw[c][j], acc); }
-      win[c][DC - 1] = xin;
-      acc = fmaf(xin, cw[c][DC - 1], acc);
+      for (int j = 0; j < DC - 1; ++j) { win[j][c] = win[j + 1][c]; acc = fmaf(win[j][c], cw[j][c], acc); }
+      win[DC - 1][c] = xin;
+      acc = fmaf(xin, cw[DC - 1][c], acc);
       cout[c] = rbf(acc / (1.0f + expf(-acc)));               // SiLU, output in the activation dtype
     }
     __syncthreads();
@@ -2084,7 +2094,7 @@ __global__ void __launch_bounds__(256) mamba_scan_kernel(ScanArgs a) {
     float yacc = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int n = quarter * 32 + j;
+      const int n = (j >> 3) * 32 + quarter * 8 + (j & 7);
       h[j] = fmaf(h[j], dA, dtx * cout[P + n]);
       yacc = fmaf(h[j], cout[P + N + n], yacc);
       if (a.T == 1) h[j] = rbf(h[j]);                            // decode: the stored state is in the cache dtype
@@ -2098,19 +2108,17 @@ __global__ void __launch_bounds__(256) mamba_scan_kernel(ScanArgs a) {
     }
     __syncthreads();
   }
-  {
-    bf16* sp = a.ssm_state + (((size_t)r * a.nheads + hh) * P + p) * N + quarter * 32;
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 v;
+  for (int j = 0; j < 32; j += 8) {
+    uint4 v;
       v.x = pack_bf16(h[j], h[j + 1]); v.y = pack_bf16(h[j + 2], h[j + 3]); v.z = pack_bf16(h[j + 4], h[j + 5]); v.w = pack_bf16(h[j + 6], h[j + 7]);
-      *reinterpret_cast<uint4*>(sp + j) = v;
-    }
+    *reinterpret_cast<uint4*>(sp + 4 * j) = v;                  // elements 32 (j / 8) + 8 quarter ...
   }
   for (int c = tid; c < CH; c += 256) {
     if (c >= P && hh != 0) continue;                              // the shared B/C channels are written once (head 0)
-    const int gc = chan(c);
-    for (int j = 0; j < DC; ++j) a.conv_state[((size_t)r * a.conv_dim + gc) * DC + j] = f2bf(win[c][j]);
+    uint2 o;
+    o.x = pack_bf16(win[0][c], win[1][c]); o.y = pack_bf16(win[2][c], win[3][c]);
+    *reinterpret_cast<uint2*>(a.conv_state + ((size_t)r * a.conv_dim + chan(c)) * DC) = o;
   }
 }
 

@@ -413,7 +413,7 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
         samples.sort()
         ttfa = {"p50_ms": samples[len(samples) // 2], "min_ms": samples[0], "max_ms": samples[-1], "chunk_frames": 43,
-                "definition": "generate_stream() entry -> first 0.5 s chunk DAC-decoded and copied to the host (prefill + 84 steps + chunk decode)"}
+                "definition": "generate_stream() entry -> first 0.5 s chunk DAC-decoded and copied to the host (prefill + 77 steps + chunk decode)"}
     del cond_dev
 
     # ---- the other half of the metric: 64 utterances per GPU (BASELINE.json configs[3]); every rank runs it ----

@@ -406,6 +406,29 @@ def test_generate_stream_equals_generate_plus_decode():
     assert wav.shape == wav_full.shape and torch.equal(wav, wav_full)
 
 
+@pytest.mark.parametrize("holdback", [25, 32])
+def test_generate_stream_with_eos_never_emits_a_cut_frame(holdback):
+    """Streaming with utterances that END (codebook-0 EOS made likely): the reference trims the result at the EOS frame it
+    finds in the last 50 positions (zonos/model.py:513-528), at most 9 + 16 frames behind the loop front when the loop
+    stops (remaining_steps = 9, stop flag read every 16 / 8 steps, tensor_ops.py:90-103).  A frame emitted once the front is
+    `holdback` >= 25 past it can therefore never be cut: chunks must concatenate to exactly generate() + decode() for
+    every seed, whatever the length."""
+    w = eos_boosted(make_backbone_weights(**TINY_DIMS, seed=11), 5.0)
+    model = build_b200_model(TINY_DIMS, w, DEV, dac_weights=make_dac_weights(seed=1))
+    cond = make_conditioning(2, 9, TINY_DIMS["d_model"]).to(DEV)
+    lengths = set()
+    for seed in range(8):
+        full = model.generate(cond, max_new_tokens=240, seed=seed)
+        wav_full = model.autoencoder.decode(full)
+        chunks = list(model.generate_stream(cond, max_new_tokens=240, seed=seed, chunk_frames=20, holdback_frames=holdback))
+        codes = torch.cat([c for _, c in chunks], dim=-1)
+        wav = torch.cat([w_ for w_, _ in chunks], dim=-1)
+        assert torch.equal(codes, full), (seed, codes.shape, full.shape)
+        assert wav.shape == wav_full.shape and torch.equal(wav, wav_full), seed
+        lengths.add(full.shape[-1])
+    assert min(lengths) < 240, "no utterance ended early: the EOS path was not exercised"
+
+
 # ------------------------------------------------------------------------------ hybrid (Mamba2) --
 def _hybrid_model(device):
     from oracle.hybrid import HybridDims, HybridOracle

@@ -324,7 +324,9 @@ zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t strea
   // few weight tiles (batch 3..8 decode: the N=2048 matrices are 16 tiles, i.e. 16 SMs would stream them alone; at
   // batch 64 split-K measured slower: 1.75 s vs 1.52 s per pass)
   static const int splitk_env = getenv("ZB_TC_SPLITK") ? atoi(getenv("ZB_TC_SPLITK")) : -1;
-  const bool splitk_on = splitk_env > 0 || (splitk_env < 0 && g.decode && g.M <= 32 && ntiles <= 48);
+  static const int splitk_maxm = getenv("ZB_TC_SPLITK_MAXM") ? atoi(getenv("ZB_TC_SPLITK_MAXM")) : 32;
+  static const int splitk_maxtiles = getenv("ZB_TC_SPLITK_MAXTILES") ? atoi(getenv("ZB_TC_SPLITK_MAXTILES")) : 48;
+  const bool splitk_on = splitk_env > 0 || (splitk_env < 0 && g.decode && g.M <= splitk_maxm && ntiles <= splitk_maxtiles);
   if (splitk_on && mtiles == 1 && ntiles < ctx->num_sms) {
     ksplit = (ctx->num_sms + ntiles - 1) / ntiles;
     const int nkb = g.K / TC_BK;

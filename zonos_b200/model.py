@@ -265,15 +265,17 @@ class Zonos(nn.Module):
     @torch.inference_mode()
     def generate_stream(self, prefix_conditioning: torch.Tensor, audio_prefix_codes: torch.Tensor | None = None,
                         max_new_tokens: int = 86 * 30, cfg_scale: float = 2.0, batch_size: int = 1,
-                        sampling_params: dict = dict(min_p=0.1), *, chunk_frames: int = 43, holdback_frames: int = 32,
+                        sampling_params: dict = dict(min_p=0.1), *, chunk_frames: int = 43, holdback_frames: int = 25,
                         seed: int | None = None):
         """Generator of (wav fp32 [B,1,512*n], codes int64 [B,9,n]) chunks: the same loop as `generate`, but finished frames
         are DAC-decoded while the loop keeps running (the reference can only decode after `generate` returns).
 
-        A frame is final once the loop front is `holdback_frames` past it: 32 >= the decoder's receptive field (so every
-        emitted sample equals the one a full decode produces) and >= the span the reference's EOS-boundary scan can still
-        cut (model.py:513-528 looks at most 9 + 16 frames behind the stop).  Time to first audio = prefill +
-        (chunk_frames + holdback_frames + 9) decode steps + one chunk decode."""
+        A frame is final once the loop front is `holdback_frames` past it: 25 >= the decoder's receptive field (16-frame halo,
+        so every emitted sample equals the one a full decode produces) and = the span the reference's EOS-boundary scan can
+        still cut (model.py:513-528: the EOS frame is at most 9 + 16 frames behind the front when the loop stops -
+        remaining_steps = 9, stop flag read every 16 / 8 steps).  Time to first audio = prefill +
+        (chunk_frames + holdback_frames + 9) decode steps + one chunk decode
+        (tests: test_generate_stream_with_eos_never_emits_a_cut_frame)."""
         assert cfg_scale != 1, "TODO: add support for cfg_scale=1"
         device = self.device
         Q, B = self.num_codebooks, batch_size

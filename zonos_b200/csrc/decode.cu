@@ -2349,7 +2349,7 @@ zb_status zb_run_layers(zb_ctx* ctx, const zb_model* model, const zb_cache* cach
   const int G = d.n_heads / d.n_heads_kv;
 
   const bool tc = M > 4 && d.d_model % 64 == 0 && d.d_ff % 64 == 0;   // dense path: tcgen05 GEMMs
-  const bool tc_qkv = tc && d.rope_interleaved;                     // (the tcgen05 QKV epilogue rotates interleaved pairs only)
+  const bool tc_qkv = tc && (d.rope_interleaved || d.head_dim == 128);   // (rotate-half pairs need one head per 128-row tile)
   auto norm_rows = [&](const bf16* w, const bf16* b) -> zb_status {
     NormArgs na;
     na.x = x; na.ldx = d.d_model; na.y = s.xn; na.ldy = d.d_model; na.w = w; na.b = b; na.D = d.d_model; na.eps = d.norm_eps; na.kind = d.norm_kind;

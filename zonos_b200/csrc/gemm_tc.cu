@@ -178,6 +178,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
         }
       }
+    } else if (a.epi == TEPI_QKV && !a.rope_interleaved) {
+      // rotate-half RoPE (flash_attn's non-interleaved convention, hybrid variant): feature i of a head pairs with i + 64.  A
+      // 128-row tile is exactly one head, so the partner sits 64 lanes away: all rows park their bf16-rounded values in
+      // shared memory (the ring is idle now), then every row reads its partner's.
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        load_chunk(c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xchg[(size_t)lr * BN + c0 + j] = rbf(v[j]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int qn = a.Hq * a.hd, kn = a.Hkv * a.hd;
+      const bool rot = n < qn + kn;
+      const int fi = (n % a.hd) % (a.hd / 2);                           // frequency index of this row and of its partner
+      for (int c = 0; c < BN; ++c) {
+        const int m = m0 + c;
+        if (m >= a.M || !n_ok) continue;
+        const int pos = a.lengths[m / a.T] + m % a.T;
+        float o = xchg[(size_t)lr * BN + c];
+        if (rot) {
+          const float other = xchg[(size_t)(lr ^ 64) * BN + c];
+          const float2 cs = *reinterpret_cast<const float2*>(a.rope + ((size_t)min(pos, a.rope_len - 1) * (a.hd / 2) + fi) * 2);
+          o = (lr & 64) ? __fadd_rn(__fmul_rn(o, cs.x), __fmul_rn(other, cs.y))      // x[i+64]*c + x[i]*s
+                        : __fsub_rn(__fmul_rn(o, cs.x), __fmul_rn(other, cs.y));     // x[i]*c - x[i+64]*s
+        }
+        if (n < qn) {
+          a.q_out[(size_t)m * qn + n] = f2bf(o);
+        } else {
+          const int kvsel = n < qn + kn ? 0 : 1;
+          const int ci = n - qn - kvsel * kn;
+          const int page = a.page_table[(size_t)(m / a.T) * a.max_pages + pos / ZB_PAGE_TOKENS];
+          bf16* pb = a.kv_layer + ((size_t)page * 2 + kvsel) * a.Hkv * ZB_PAGE_TOKENS * a.hd;
+          pb[((size_t)(ci / a.hd) * ZB_PAGE_TOKENS + pos % ZB_PAGE_TOKENS) * a.hd + (ci % a.hd)] = f2bf(o);
+        }
+      }
     } else {
       for (int c0 = 0; c0 < BN; c0 += 16) {
         float v[16];
@@ -306,7 +341,7 @@ zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t strea
   a.T = g.T; a.Hq = g.Hq; a.Hkv = g.Hkv; a.hd = g.hd; a.rope_interleaved = g.rope_interleaved; a.rope_len = g.rope_len;
   a.max_pages = g.max_pages; a.rope = g.rope; a.lengths = g.lengths; a.page_table = g.page_table; a.kv_layer = g.kv_layer; a.q_out = g.q_out;
   a.B = g.B; a.cfg_scale = g.cfg_scale; a.logits = g.logits; a.QV = g.QV;
-  ZB_REQUIRE(ctx, g.epi != TEPI_QKV || g.rope_interleaved, "gemm_tc: rotate-half RoPE epilogue is not implemented");
+  ZB_REQUIRE(ctx, g.epi != TEPI_QKV || g.rope_interleaved || g.hd == TC_BM, "gemm_tc: the rotate-half RoPE epilogue needs one head per 128-row tile");
   if (zb_status st = make_map_2d(ctx, &a.map_w, g.W, g.N, g.K, g.K, 64)) return st;
   if (zb_status st = make_map_2d(ctx, &a.map_x, g.x, g.M, g.K, g.ldx, BN)) return st;
   const int a_bytes = TC_BM * TC_BK * 2, b_bytes = ((BN * TC_BK * 2 + 1023) / 1024) * 1024;

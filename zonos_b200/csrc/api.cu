@@ -89,6 +89,8 @@ zb_status zb_ctx_destroy(zb_ctx* ctx) {
   for (zb_gen_slab& sl : ctx->gen_slabs) {
     if (sl.dev) cudaFree(sl.dev);
     if (sl.host) cudaFreeHost(sl.host);
+    if (sl.stage) cudaFreeHost(sl.stage);
+    if (sl.stage_ev) cudaEventDestroy(sl.stage_ev);
   }
   delete ctx;
   return ZB_OK;
@@ -316,8 +318,19 @@ zb_status zb_generate_begin(zb_ctx* ctx, const zb_model* model, const zb_cache* 
       if (zb_status st = g->tc ? zb_tc_table_build(ctx, model, cache, R, g->mega_arena, hb.data()) : zb_mega_layers_build(ctx, model, cache, hb.data(), s)) return fail(st);
       if (sl.layers != hb || sl.layers_off != o_layers) {  // same model and cache as the slab's last session: already there
         sl.layers = hb; sl.layers_off = o_layers;
-        G_CUDA(cudaMemcpyAsync(g->mega_layers, sl.layers.data(), hb.size(), cudaMemcpyHostToDevice, s));
-        G_CUDA(cudaStreamSynchronize(s));                 // pageable source: keep the copy simple and finished
+        // a fresh KV allocation per generate() changes the table every call: stage it in pinned memory so the upload
+        // needs no stream synchronisation (the event only guards the staging buffer against being rewritten too early)
+        if (sl.stage_bytes < hb.size()) {
+          if (sl.stage) { G_CUDA(cudaEventSynchronize(sl.stage_ev)); G_CUDA(cudaFreeHost(sl.stage)); sl.stage = nullptr; sl.stage_bytes = 0; }
+          G_CUDA(cudaHostAlloc(&sl.stage, hb.size(), cudaHostAllocDefault));
+          sl.stage_bytes = hb.size();
+          if (!sl.stage_ev) G_CUDA(cudaEventCreateWithFlags(&sl.stage_ev, cudaEventDisableTiming));
+        } else {
+          G_CUDA(cudaEventSynchronize(sl.stage_ev));
+        }
+        memcpy(sl.stage, hb.data(), hb.size());
+        G_CUDA(cudaMemcpyAsync(g->mega_layers, sl.stage, hb.size(), cudaMemcpyHostToDevice, s));
+        G_CUDA(cudaEventRecord(sl.stage_ev, s));
       }
       G_CUDA(cudaMemsetAsync(g->mega_bar, 0, 256, s));
       G_CUDA(cudaMemsetAsync(g->mega_arena, 0, arena_bytes, s));   // tag 0 = never written (decode.cu) / arrival counters (decode_tc.cu)

@@ -23,6 +23,8 @@ typedef __nv_bfloat16 bf16;
 struct zb_gen_slab {
   void* dev = nullptr; size_t dev_bytes = 0; int32_t* host = nullptr; int32_t* host_dev = nullptr; bool in_use = false;
   std::vector<unsigned char> layers; size_t layers_off = 0;   // host copy of the layer table last uploaded into this slab
+  // pinned staging of that table: the upload is asynchronous; `stage_ev` marks the last copy OUT of the staging buffer
+  void* stage = nullptr; size_t stage_bytes = 0; cudaEvent_t stage_ev = nullptr;
 };
 
 struct zb_ctx {

@@ -348,9 +348,19 @@ zb_status zb_launch_gemm_tc(zb_ctx* ctx, const zb_gemm_tc& g, cudaStream_t strea
   int stages = (200 * 1024) / (a_bytes + b_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
+  // epilogue exchange buffer (reuses the ring): gate rows for SiLU, whole tiles for the CFG mix and the rotate-half RoPE
+  const size_t xchg = g.epi == TEPI_SILU ? (size_t)64 * BN * 4
+                    : (g.epi == TEPI_HEADS && g.cfg_scale != 1.0f) || (g.epi == TEPI_QKV && !g.rope_interleaved) ? (size_t)128 * BN * 4 : 0;
+  // Many m-tiles (prefill): TWO CTAs per SM, so that the epilogue of one tile (RoPE + KV append, SiLU: as long as its main
+  // loop) overlaps the MMAs of another - 2 x <= 113 KB of shared memory, 2 x <= 256 TMEM columns
+  static const int two_cta = getenv("ZB_TC_TWO_CTA") ? atoi(getenv("ZB_TC_TWO_CTA")) : 1;
+  if (two_cta && mtiles >= 4 && xchg + 1024 <= 112 * 1024) {
+    const int s2 = (int)((112 * 1024 - 1024) / (a_bytes + b_bytes));
+    if (s2 >= 2) stages = std::min(stages, s2);
+  }
   a.stages = stages;
   size_t smem = (size_t)stages * (a_bytes + b_bytes) + 1024;
-  if ((size_t)128 * BN * 4 + 1024 > smem) smem = (size_t)128 * BN * 4 + 1024;     // epilogue exchange buffer reuses the ring
+  if (xchg + 1024 > smem) smem = xchg + 1024;
   ZB_CUDA(ctx, zb_ensure_smem(ctx, gemm_tc_kernel, smem));
   const int ntiles = (g.epi == TEPI_SILU) ? (g.F + 63) / 64 : (g.N + TC_BM - 1) / TC_BM;
   // split-K for the bandwidth-bound small-M regime: enough CTAs to pull weights with every SM

@@ -1,3 +1,5 @@
+#!/bin/bash
+# Round-end check on a GPU box (under gpurun): the GPU test suite, smoke(), the default bench line and BASELINE.json configs[4].
 set -u
 O=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > $O/r2_gputest_final.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r2_gputest_final.log

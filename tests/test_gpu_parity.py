@@ -289,6 +289,23 @@ def test_generate_mega_tcgen05_consumer_golden(case, monkeypatch):
     test_generate_matches_reference_golden(case)
 
 
+def test_in_place_weight_update_reaches_the_derived_copies(monkeypatch):
+    """The tcgen05 consumer of the persistent kernel streams a tile-ordered COPY of the weights.  `load_state_dict` after the
+    first call writes the parameters in place (same pointers): torch's version counters must invalidate the copy
+    (zb_model_weights_changed), i.e. the second result equals a fresh model's, not the first one."""
+    monkeypatch.setenv("ZB_MEGA_TC", "1")
+    w1, w2 = make_backbone_weights(**TINY_DIMS, seed=11), make_backbone_weights(**TINY_DIMS, seed=12)
+    model = build_b200_model(TINY_DIMS, w1, DEV)
+    cond = make_conditioning(2, 10, TINY_DIMS["d_model"], seed=9).to(DEV)
+    q = q_stream_from_seed(3, 12 + 9, 1)
+    first = model.generate(cond, max_new_tokens=12, batch_size=1, q_stream=q)
+    model.load_state_dict(w2)
+    second = model.generate(cond, max_new_tokens=12, batch_size=1, q_stream=q)
+    fresh = build_b200_model(TINY_DIMS, w2, DEV).generate(cond, max_new_tokens=12, batch_size=1, q_stream=q)
+    assert torch.equal(second, fresh)
+    assert not torch.equal(first, second)
+
+
 def test_generate_tcgen05_eos_and_prefix_golden(monkeypatch):
     """The reference-recorded B=2 case with an audio prefix, EOS and the unified sampler, through decode_tc.cu."""
     monkeypatch.setenv("ZB_DECODE_TC", "2")

@@ -170,7 +170,8 @@ class B200ZonosBackbone(nn.Module):
         hit = self._handles.get(key)
         # torch bumps a tensor's version on every in-place write (load_state_dict, optimizer steps): same pointers, new
         # values - the library must rebuild what it derived from the weights (zb_model_weights_changed)
-        versions = tuple(p._version for p in self.parameters())
+        versions = tuple(p._version for p in self.parameters()) + tuple(e._version for e in (embeddings or [])) + \
+            ((heads._version,) if heads is not None else ())
         if hit is not None:
             if self._versions.get(key) != versions:
                 _lib.load().zb_model_weights_changed(hit[0])

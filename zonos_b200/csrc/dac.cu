@@ -121,17 +121,24 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(ConvArgs a) {
 // A is fetched by a 3-D TMA box {64 channels, 128 time steps, 1 batch} at time offset j0 + shift(tap): rows outside
 // [0, Lin) are zero-filled by the TMA unit, which IS the convolution's zero padding (per batch element).
 //   warp 4: TMA producer | warp 5: TMEM alloc + tcgen05.mma issuer | warps 0-3: epilogue (lane <-> time row)
+// Halo mode (stride-1 convs with several taps): the taps of one 64-channel chunk read the SAME time rows shifted by
+// tap * dilation, so the chunk's rows [j0 - pad, j0 - pad + 128 + (taps - 1) * dil) are fetched ONCE (box {64, halo_rows, 1},
+// double-buffered) and every tap's A operand is that tile with the descriptor's start address moved down tap * dil rows: a
+// K-major SWIZZLE_128B operand may start at any row, the swizzle being a function of the absolute shared-memory address
+// (scripts/probes/desc_shift_probe.cu).  The ring then only carries the weight tiles: a k = 7 conv was bound by the
+// L2 -> SM port with 7 x 16 KB of activations + 7 weight tiles per chunk (ncu, profiles/r2_ncu_full_conv_tc.txt).
 constexpr int CV_THREADS = 192;
 struct ConvTcArgs {
   CUtensorMap map_in;   // activations [B][Lin][in_ld], box {64, 128, 1}
   CUtensorMap map_w;    // weights [taps*N][in_ld], box {64, BN}
   ConvArgs c;
   int BN, stages;
+  int halo_rows;        // > 0: "halo" mode, see conv_tc_kernel
 };
 
 __global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_constant__ ConvTcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem_cv[];
-  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar, hfull[2], hempty[2];
   __shared__ uint32_t tmem_base_smem;
   const ConvArgs& a = p.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,8 +153,12 @@ __global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar, 1);
+    mbar_init(&hfull[0], 1); mbar_init(&hfull[1], 1); mbar_init(&hempty[0], 1); mbar_init(&hempty[1], 1);
     mbar_fence_init();
   }
+  // halo mode: two halo tiles, then the ring of weight tiles
+  const int halo_bytes = ((p.halo_rows * 128 + 1023) / 1024) * 1024, w_bytes = ((b_bytes + 1023) / 1024) * 1024;
+  unsigned char* wring = base + 2 * (size_t)halo_bytes;
   uint32_t ncols = 32;
   while ((int)ncols < BN) ncols <<= 1;
   if (warp == 5) {
@@ -159,7 +170,48 @@ __global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp == 4) {
+  if (warp == 4 && p.halo_rows > 0) {
+    if (lane == 0) {
+      int wst = 0;
+      for (int c = 0; c < kchunks; ++c) {
+        const int hb = c & 1;
+        if (c >= 2) mbar_wait(&hempty[hb], ((c >> 1) - 1) & 1);
+        mbar_expect_tx(&hfull[hb], (uint32_t)(p.halo_rows * 128));      // rows outside [0, Lin) are zero-filled and still counted
+        tma_load_3d(base + (size_t)hb * halo_bytes, &p.map_in, c * 64, j0 - a.pad, b, &hfull[hb]);
+        for (int tap = 0; tap < a.taps; ++tap, ++wst) {
+          const int s = wst % p.stages;
+          if (wst >= p.stages) mbar_wait(&empty_bar[s], ((wst / p.stages) - 1) & 1);
+          mbar_expect_tx(&full_bar[s], (uint32_t)b_bytes);
+          tma_load_2d(wring + (size_t)s * w_bytes, &p.map_w, c * 64, tap * a.N + n0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (p.halo_rows > 0 && warp_id_uniform() == 5) {
+    const uint32_t idesc = make_idesc(128, BN);
+    int wst = 0;
+    for (int c = 0; c < kchunks; ++c) {
+      const int hb = c & 1;
+      mbar_wait(&hfull[hb], (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ha = smem_u32(base + (size_t)hb * halo_bytes);
+      for (int tap = 0; tap < a.taps; ++tap, ++wst) {
+        const int s = wst % p.stages;
+        mbar_wait(&full_bar[s], (wst / p.stages) & 1);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc(ha + (uint32_t)(tap * a.dil) * 128u);     // the tap's rows: tile start moved down tap * dil rows
+        const uint64_t db = make_smem_desc(smem_u32(wring + (size_t)s * w_bytes));
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | tap | kk) ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+          if (tap == a.taps - 1) tc_commit(&hempty[hb]);     // every tap of the chunk has read the halo tile
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tc_commit(&tmem_full_bar);
+    __syncwarp();
+  } else if (warp == 4) {
     if (lane == 0) {
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % p.stages;
@@ -410,7 +462,12 @@ zb_status run_conv(zb_ctx* ctx, const zb_conv_w& c, const bf16* in, int B, int L
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.in_ld, (cuuint64_t)Lin, (cuuint64_t)B};
     cuuint64_t str[2] = {(cuuint64_t)a.in_ld * 2, (cuuint64_t)Lin * a.in_ld * 2};
-    cuuint32_t box[3] = {64, 128, 1};
+    // opt-in: measured 344.7 against 345.5 ms for 64 x 861 frames - fetching each chunk's rows once instead of once per tap cuts
+    // the L2 -> SM traffic of a k = 7 conv by a third to a half, but the kernel is not bound by it
+    static const int env_halo = getenv("ZB_DAC_HALO") ? atoi(getenv("ZB_DAC_HALO")) : 0;
+    const int halo_rows = 128 + (c.taps - 1) * c.dil;
+    p.halo_rows = (env_halo && !c.ups && c.taps > 1 && halo_rows <= 256) ? halo_rows : 0;
+    cuuint32_t box[3] = {64, (cuuint32_t)(p.halo_rows ? p.halo_rows : 128), 1};
     if (zb_status st = make_map(ctx, &p.map_in, in, 3, dims, str, box)) return st;
   }
   {
@@ -427,11 +484,16 @@ zb_status run_conv(zb_ctx* ctx, const zb_conv_w& c, const bf16* in, int B, int L
   if (env_ctas > 0) ctas = std::min(env_ctas, bn <= 128 ? 4 : 2);
   const int nk_total = c.taps * (a.in_ld / 64);
   int stages = ((220 * 1024) / ctas - 1024) / (a_bytes + b_bytes);
+  size_t halo_smem = 0;
+  if (p.halo_rows) {                                          // two halo tiles + a ring of weight tiles only
+    halo_smem = 2 * (size_t)(((p.halo_rows * 128 + 1023) / 1024) * 1024);
+    stages = (int)(((220 * 1024) / ctas - 1024 - (long)halo_smem) / b_bytes);
+  }
   if (stages > 8) stages = 8;
   if (stages > nk_total) stages = nk_total;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * (a_bytes + b_bytes) + 1024;
+  const size_t smem = p.halo_rows ? halo_smem + (size_t)stages * b_bytes + 1024 : (size_t)stages * (a_bytes + b_bytes) + 1024;
   ZB_CUDA(ctx, zb_ensure_smem(ctx, conv_tc_kernel, smem));
   dim3 grid((a.rows + 127) / 128, ntiles, B);
   conv_tc_kernel<<<grid, CV_THREADS, smem, s>>>(p);

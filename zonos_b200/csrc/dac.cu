@@ -36,14 +36,16 @@ struct ConvArgs {
 // Cody-Waite reduction (exact product k * pi_hi for |k| < 2^11, error ~ k * 1e-15 beyond) + the SFU sine on [-pi/2, pi/2]
 // (abs error 2^-21, far below the bf16 rounding that follows).  sinf()'s slow path (arguments > 1e5, local memory) made
 // the epilogue the bottleneck of the decoder on saturated activations; the reciprocal is IEEE-rounded like torch's.
-__device__ __forceinline__ float snake_f(float x, float alpha) {
+// inv = __frcp_rn(alpha + 1e-9f): a per-channel constant, computed once per CTA by the tensor-core kernel's epilogue
+__device__ __forceinline__ float snake_inv(float x, float alpha, float inv) {
   const float y = alpha * x;
   const float k = rintf(y * 0.318309886183790672f);
   float r = fmaf(-k, 3.140625f, y);                            // pi = 3.140625 + 9.67653589793e-4 (hi has 8 significant bits)
   r = fmaf(-k, 9.67653589793e-4f, r);
   const float sn = __sinf(r);
-  return x + __frcp_rn(alpha + 1e-9f) * (sn * sn);
+  return x + inv * (sn * sn);
 }
+__device__ __forceinline__ float snake_f(float x, float alpha) { return snake_inv(x, alpha, __frcp_rn(alpha + 1e-9f)); }
 
 constexpr int BM = 64, BN = 64, BK = 32;
 
@@ -140,6 +142,9 @@ __global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_con
   extern __shared__ __align__(1024) unsigned char smem_cv[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar, hfull[2], hempty[2];
   __shared__ uint32_t tmem_base_smem;
+  // per-column constants of this CTA's output tile (plain convs): bias, Snake alpha and its IEEE reciprocal - fetched and
+  // computed once per CTA while the main loop runs instead of once per element (two global loads + a reciprocal each)
+  __shared__ __align__(16) float s_bias[256], s_alpha[256], s_inv[256];
   const ConvArgs& a = p.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
@@ -245,9 +250,18 @@ __global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_con
     __syncwarp();
   } else {
     // ===== epilogue: lane <-> GEMM row j (time), 16 output columns per TMEM read =====
+    const int j = j0 + warp * 32 + lane;
+    {
+      for (int c = threadIdx.x; c < BN; c += 128) {
+        const int n = n0 + c, co = a.ups ? n % a.Cout : n;        // transposed conv: GEMM column = phase * Cout + channel
+        const bool ok = n < a.N;
+        const float al = (a.alpha && ok) ? a.alpha[co] : 1.f;
+        s_bias[c] = ok ? a.bias[co] : 0.f; s_alpha[c] = al; s_inv[c] = __frcp_rn(al + 1e-9f);
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");          // the four epilogue warps
+    }
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
-    const int j = j0 + warp * 32 + lane;
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
@@ -270,10 +284,11 @@ __global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_con
         uint32_t raw[8], act[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float x0 = rbf(v[2 * q] + a.bias[co0 + 2 * q]), x1 = rbf(v[2 * q + 1] + a.bias[co0 + 2 * q + 1]);
+          const int cl = c0 + 2 * q;                              // column inside the tile: constants from shared memory (broadcast reads)
+          float x0 = rbf(v[2 * q] + s_bias[cl]), x1 = rbf(v[2 * q + 1] + s_bias[cl + 1]);
           if (a.resid) { x0 = rbf(r[2 * q] + x0); x1 = rbf(r[2 * q + 1] + x1); }
           raw[q] = pack_bf16(x0, x1);
-          act[q] = a.alpha ? pack_bf16(snake_f(x0, a.alpha[co0 + 2 * q]), snake_f(x1, a.alpha[co0 + 2 * q + 1])) : raw[q];
+          act[q] = a.alpha ? pack_bf16(snake_inv(x0, s_alpha[cl], s_inv[cl]), snake_inv(x1, s_alpha[cl + 1], s_inv[cl + 1])) : raw[q];
         }
         if (a.out_raw) {
           *reinterpret_cast<uint4*>(a.out_raw + o) = make_uint4(raw[0], raw[1], raw[2], raw[3]);
@@ -300,10 +315,10 @@ __global__ void __launch_bounds__(CV_THREADS, 3) conv_tc_kernel(const __grid_con
           if (a.ups) { const int ph = n / a.Cout; co = n % a.Cout; t2 = a.ups * j + ph - a.pad; }
           if (t2 < 0 || t2 >= a.Lout) continue;
           const size_t o = ((size_t)b * a.Lout + t2) * a.out_ld + co;
-          float x0 = rbf(v[q] + a.bias[co]);
+          float x0 = rbf(v[q] + s_bias[c0 + q]);
           if (a.resid) x0 = rbf(bf2f(a.resid[o]) + x0);
           if (a.out_raw) a.out_raw[o] = f2bf(x0);
-          if (a.out_act) a.out_act[o] = f2bf(a.alpha ? snake_f(x0, a.alpha[co]) : x0);
+          if (a.out_act) a.out_act[o] = f2bf(a.alpha ? snake_inv(x0, s_alpha[c0 + q], s_inv[c0 + q]) : x0);
           if (co == a.Cout - 1 && a.out_ld > a.Cout) {
             for (int cz = a.Cout; cz < a.out_ld; ++cz) {
               const size_t oz = ((size_t)b * a.Lout + t2) * a.out_ld + cz;

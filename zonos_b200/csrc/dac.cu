@@ -477,9 +477,8 @@ zb_status run_conv(zb_ctx* ctx, const zb_conv_w& c, const bf16* in, int B, int L
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.in_ld, (cuuint64_t)Lin, (cuuint64_t)B};
     cuuint64_t str[2] = {(cuuint64_t)a.in_ld * 2, (cuuint64_t)Lin * a.in_ld * 2};
-    // opt-in: measured 344.7 against 345.5 ms for 64 x 861 frames - fetching each chunk's rows once instead of once per tap cuts
-    // the L2 -> SM traffic of a k = 7 conv by a third to a half, but the kernel is not bound by it
-    static const int env_halo = getenv("ZB_DAC_HALO") ? atoi(getenv("ZB_DAC_HALO")) : 0;
+    // 64 x 861 frames: 225.8 -> 209.9 ms (no gain while the epilogue was the bound: 345.5 -> 344.7)
+    static const int env_halo = getenv("ZB_DAC_HALO") ? atoi(getenv("ZB_DAC_HALO")) : 1;
     const int halo_rows = 128 + (c.taps - 1) * c.dil;
     p.halo_rows = (env_halo && !c.ups && c.taps > 1 && halo_rows <= 256) ? halo_rows : 0;
     cuuint32_t box[3] = {64, (cuuint32_t)(p.halo_rows ? p.halo_rows : 128), 1};

@@ -406,30 +406,33 @@ __device__ __forceinline__ void tc_gemm_compute(const TcArgs& a, int kind, uint6
 }
 
 // ---- element-wise sub-phase: sum the K-slice partials in slice order, fused epilogue -------------------------------
+template <int NB>
+__device__ __forceinline__ void sum_partials_batch(const float*& p, size_t stride, float (&v)[8]) {
+  float4 lo[NB], hi[NB];
+#pragma unroll
+  for (int e = 0; e < NB; ++e) {
+    lo[e] = __ldcg(reinterpret_cast<const float4*>(p + e * stride));
+    hi[e] = __ldcg(reinterpret_cast<const float4*>(p + e * stride + 4));
+  }
+#pragma unroll
+  for (int e = 0; e < NB; ++e) {
+    v[0] += lo[e].x; v[1] += lo[e].y; v[2] += lo[e].z; v[3] += lo[e].w; v[4] += hi[e].x; v[5] += hi[e].y; v[6] += hi[e].z; v[7] += hi[e].w;
+  }
+  p += NB * stride;
+}
 __device__ __forceinline__ void sum_partials(const TcArgs& a, const TcGemm& g, int m, int n0, float (&v)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
   const size_t stride = (size_t)a.R * g.Nw;
   const float* p = a.ws + (size_t)m * g.Nw + n0;
-  int ks = 0;
-  // four slices per round: the eight loads are in flight together (one L2 round trip instead of four); the additions
-  // keep the slice order
-  for (; ks + 4 <= g.nks; ks += 4, p += 4 * stride) {
-    float4 lo[4], hi[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      lo[e] = __ldcg(reinterpret_cast<const float4*>(p + e * stride));
-      hi[e] = __ldcg(reinterpret_cast<const float4*>(p + e * stride + 4));
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      v[0] += lo[e].x; v[1] += lo[e].y; v[2] += lo[e].z; v[3] += lo[e].w; v[4] += hi[e].x; v[5] += hi[e].y; v[6] += hi[e].z; v[7] += hi[e].w;
-    }
-  }
-  for (; ks < g.nks; ++ks, p += stride) {
-    const float4 a0 = __ldcg(reinterpret_cast<const float4*>(p)), a1 = __ldcg(reinterpret_cast<const float4*>(p + 4));
-    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-  }
+  // batches of 8 / 4 / 2 / 1 slices whose loads are in flight together: the reduce + epilogue sub-phases are chains of L2 round
+  // trips on the critical path of every GEMM (9 slices: 2 round trips, 3 with batches of 4); the additions keep the slice
+  // order, so the result does not depend on how the loads are batched
+  int left = g.nks;
+  while (left >= 8) { sum_partials_batch<8>(p, stride, v); left -= 8; }
+  if (left >= 4) { sum_partials_batch<4>(p, stride, v); left -= 4; }
+  if (left >= 2) { sum_partials_batch<2>(p, stride, v); left -= 2; }
+  if (left >= 1) sum_partials_batch<1>(p, stride, v);
 }
 
 __device__ __forceinline__ uint4 norm8(const uint4& v, float mean, float rstd, const uint4& gw, const uint4& gb) {
@@ -448,6 +451,11 @@ __device__ __forceinline__ uint4 norm8(const uint4& v, float mean, float rstd, c
 // (s, q): this thread's sums over its own elements of the row.  Uniform per CTA (contains CTA barriers).
 __device__ __forceinline__ void row_norm_store(const TcArgs& a, int m, int copies, int stride, float s, float q, const bf16* nw, const bf16* nb,
                                                float* red, int cw, int lane, int ctid) {
+  // norm parameters of this thread's first chunk: fetched before the barriers (they do not depend on the statistics)
+  const int n0p = ctid * 8;
+  const bool pre = n0p < a.D;
+  const uint4 gw0 = pre ? __ldg(reinterpret_cast<const uint4*>(nw + n0p)) : make_uint4(0, 0, 0, 0);
+  const uint4 gb0 = (pre && nb) ? __ldg(reinterpret_cast<const uint4*>(nb + n0p)) : make_uint4(0, 0, 0, 0);
   s = warp_sum(s); q = warp_sum(q);
   if (lane == 0) { red[2 * cw] = s; red[2 * cw + 1] = q; }
   cbar();
@@ -462,8 +470,8 @@ __device__ __forceinline__ void row_norm_store(const TcArgs& a, int m, int copie
   const float rstd = rsqrtf(var + a.eps);
   for (int n0 = ctid * 8; n0 < a.D; n0 += kCThreads * 8) {
     const uint4 xv = *reinterpret_cast<const uint4*>(a.x + (size_t)m * a.D + n0);      // written by this very thread
-    const uint4 gw = __ldg(reinterpret_cast<const uint4*>(nw + n0));
-    const uint4 gb = nb ? __ldg(reinterpret_cast<const uint4*>(nb + n0)) : make_uint4(0, 0, 0, 0);
+    const uint4 gw = n0 == n0p ? gw0 : __ldg(reinterpret_cast<const uint4*>(nw + n0));
+    const uint4 gb = n0 == n0p ? gb0 : (nb ? __ldg(reinterpret_cast<const uint4*>(nb + n0)) : make_uint4(0, 0, 0, 0));
     const uint4 o = norm8(xv, mu, rstd, gw, gb);
     for (int c = 0; c < copies; ++c) *reinterpret_cast<uint4*>(a.xn + (size_t)(m + c * stride) * a.D + n0) = o;
   }
@@ -476,9 +484,9 @@ __device__ __forceinline__ void tc_epi_resid(const TcArgs& a, int kind, const bf
     float s = 0.f, q = 0.f;
     for (int n0 = ctid * 8; n0 < a.D; n0 += kCThreads * 8) {
       float v[8];
-      sum_partials(a, g, m, n0, v);
       bf16* xp = a.x + (size_t)m * a.D + n0;
-      const uint4 old = ldcg16(xp);
+      const uint4 old = ldcg16(xp);                              // (issued with the partial sums' loads: one round trip, not two)
+      sum_partials(a, g, m, n0, v);
       const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
       uint32_t o[4];
 #pragma unroll
@@ -532,6 +540,19 @@ __device__ __forceinline__ void tc_epi(const TcArgs& a, int kind, int epi, bf16*
     const int m = t / nseg, seg = t % nseg;
     const int n0 = seg * kSegN + lane * 8;
     const bool on = n0 < nout;
+    // E_QKV: position, RoPE cos / sin and the KV page depend on the row only: fetched BEFORE the partial sums, whose loads then
+    // overlap them (three dependent L2 round trips after the sums otherwise)
+    int q_pos = 0, q_page = 0;
+    float4 q_c0 = make_float4(1.f, 0.f, 1.f, 0.f), q_c1 = q_c0;
+    if (epi == E_QKV) {
+      q_pos = a.lengths[m];
+      const int qn_ = a.Hq * kHd, kn_ = a.Hkv * kHd;
+      if (a.rope_interleaved && on && n0 < qn_ + kn_) {
+        const float* rp_ = a.rope + (size_t)min(q_pos, a.rope_len - 1) * kHd + n0 % kHd;
+        q_c0 = *reinterpret_cast<const float4*>(rp_); q_c1 = *reinterpret_cast<const float4*>(rp_ + 4);
+      }
+      if (on && n0 >= qn_) q_page = a.page_table[(size_t)m * a.max_pages + q_pos / ZB_PAGE_TOKENS];
+    }
     float v[8];
     if (on) sum_partials(a, g, m, n0, v);
     else {
@@ -564,7 +585,7 @@ __device__ __forceinline__ void tc_epi(const TcArgs& a, int kind, int epi, bf16*
       }
     } else if (epi == E_QKV) {
       const int qn = a.Hq * kHd, kn = a.Hkv * kHd;
-      const int pos = a.lengths[m];
+      const int pos = q_pos;
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = rbf(v[j]);
@@ -573,7 +594,7 @@ __device__ __forceinline__ void tc_epi(const TcArgs& a, int kind, int epi, bf16*
       const float* rp = a.rope + (size_t)min(pos, a.rope_len - 1) * kHd;      // [hd/2][2] floats
       if (a.rope_interleaved) {
         if (rot) {                                            // pairs (2i, 2i+1), un-contracted fp32 (_torch.py:57-68)
-          const float4 c0 = *reinterpret_cast<const float4*>(rp + dh), c1 = *reinterpret_cast<const float4*>(rp + dh + 4);
+          const float4 c0 = q_c0, c1 = q_c1;
           const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -606,7 +627,7 @@ __device__ __forceinline__ void tc_epi(const TcArgs& a, int kind, int epi, bf16*
         } else {
           const int kvsel = n0 < qn + kn ? 0 : 1;
           const int ci = n0 - qn - kvsel * kn;
-          const int page = a.page_table[(size_t)m * a.max_pages + pos / ZB_PAGE_TOKENS];
+          const int page = q_page;
           bf16* pb = kv_layer + (((size_t)page * 2 + kvsel) * a.Hkv + ci / kHd) * ZB_PAGE_TOKENS * kHd;
           *reinterpret_cast<uint4*>(pb + (size_t)(pos % ZB_PAGE_TOKENS) * kHd + (ci % kHd)) = pk;
         }

@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-batch64", action="store_true", help="skip the 64-utterances-per-GPU leg")
     ap.add_argument("--batch64-steps", type=int, default=2)
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the informative reference-torch-on-this-GPU timing")
+    ap.add_argument("--no-fp8", action="store_true", help="skip the opt-in FP8 leg of the default run")
     ap.add_argument("--layers", type=int, default=26, help="(debug) fewer layers; invalidates the number")
     return ap.parse_args()
 
@@ -68,7 +69,9 @@ def config_dict(args, n_gpus, batch=None, variant=None):
                            " after a %d-frame audio prefix" % args.prefix_frames if args.prefix_frames else ""),
             "baseline_config": base, "variant": variant, "prefix_frames": args.prefix_frames,
             "batch_per_gpu": batch, "frames": args.frames, "cond_len": args.cond_len, "cfg_scale": 2.0,
-            "sampling": "min_p=0.1, repetition_penalty=3.0 (generate defaults)", "n_layer": args.layers,
+            "sampling": "min_p=0.1, repetition_penalty=3.0 (generate defaults)",
+            # the hybrid leg runs the assumed shape of configs/zonos_v0.1_hybrid.json (46 layers, attention at every 9th)
+            "n_layer": 46 if variant == "hybrid" else args.layers,
             "parallelism": "request-sharded replicas x%d, no data-path collective" % n_gpus,
             "l2": "each decode step streams 3.2 GB of weights (>> 126 MB L2), no flush needed"}
 
@@ -397,6 +400,7 @@ def run_b200(args):
                                   "us_per_launch": fc1_us, "achieved_gbs": fc1_bytes / (fc1_us * 1e-6) / 1e9,
                                   "frac": fc1_bytes / (fc1_us * 1e-6) / 1e9 / peak}
 
+    default_run_early = B == 1 and args.variant == "transformer" and not P
     # ---- p50 time to first audio: generate_stream() entry -> first 43-frame (0.5 s) chunk decoded and on the host.  The
     # reference has no streaming (its TTFA is the whole generate + decode). ----
     ttfa = None
@@ -414,8 +418,6 @@ def run_b200(args):
         samples.sort()
         ttfa = {"p50_ms": samples[len(samples) // 2], "min_ms": samples[0], "max_ms": samples[-1], "chunk_frames": 43,
                 "definition": "generate_stream() entry -> first 0.5 s chunk DAC-decoded and copied to the host (prefill + 77 steps + chunk decode)"}
-    del cond_dev
-
     # ---- the other half of the metric: 64 utterances per GPU (BASELINE.json configs[3]); every rank runs it ----
     batch64 = None
     default_run = B == 1 and args.variant == "transformer" and not P
@@ -467,6 +469,59 @@ def run_b200(args):
         except Exception as e:
             ref_gpu = {"unavailable": repr(e)[:300]}
 
+    # ---- opt-in FP8 weight mode of the batch-1 decode step (ZB_FP8=1: e4m3 copy with power-of-two row scales,
+    # HFMA2 consumer; prefill and DAC stay bf16).  Reported beside the bf16 headline with its own tolerance figures, never mixed in. ----
+    fp8 = None
+    if rank == 0 and default_run_early and not args.no_fp8:
+        try:
+            def gen1(n_frames, seed, sp, trace=None):
+                return model.generate(cond_dev, None, max_new_tokens=n_frames, cfg_scale=2.0, batch_size=1, sampling_params=sp, seed=seed, trace=trace)
+
+            def timed_gen(n_frames):
+                gen1(n_frames, 5, dict(min_p=0.1))
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for r_ in range(2):
+                    gen1(n_frames, 6 + r_, dict(min_p=0.1))
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                return e0.elapsed_time(e1) / 2
+
+            n_tol = min(500, N)
+            tr_b, tr_f = {}, {}
+            greedy_b = gen1(n_tol, 3, dict(temperature=0.0), tr_b).cpu()
+            os.environ["ZB_FP8"] = "1"
+            greedy_f = gen1(n_tol, 3, dict(temperature=0.0), tr_f).cpu()
+            n_small = max(8, N // 8)
+            t_full, t_small = timed_gen(N), timed_gen(n_small)
+            step_ms = (t_full - t_small) / (N - n_small)
+            lb, lf = tr_b["logits"][1].float().cpu(), tr_f["logits"][1].float().cpu()    # first decode step: same history in both modes
+            fin = torch.isfinite(lb) & torch.isfinite(lf)
+            err = (lf - lb)[fin]
+            n_cmp = min(greedy_b.shape[-1], greedy_f.shape[-1])
+            same = (greedy_b[..., :n_cmp] == greedy_f[..., :n_cmp]).all(dim=1)[0]
+            fork = int((~same).nonzero()[0]) if (~same).any() else n_cmp
+            wq_bytes = spec0["w_bytes"] // 2
+            mean_s = Lc + 1 + (n_small + N + 16) / 2
+            step_bytes = wq_bytes + 2 * mean_s * spec0["kv_tok"] + 2 * spec0["kv_tok"] + 9 * spec0["d_model"] * 2 + 9 * 1025 * 4
+            fp8 = {"value": (N / FRAME_RATE) / (t_full / 1e3 + head["breakdown_ms"]["dac_ms"] / 1e3), "unit": UNIT,
+                   "us_per_decode_step": step_ms * 1e3, "speedup_of_the_step_vs_bf16": head["roofline"]["us_per_launch"] / (step_ms * 1e3),
+                   "roofline": {"bound": "hbm", "kernel": "decode_step_kernel<R=2, FP8 mode> (e4m3 weights, HFMA2 consumer) + sample kernel",
+                                "algorithmic_bytes_per_launch": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": peak,
+                                "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
+                   "tolerance": {"first_decode_step_logits_vs_bf16": {"rms_err": float(err.pow(2).mean().sqrt()), "max_abs_err": float(err.abs().max()),
+                                                                      "rms_of_bf16_logits": float(lb[fin].pow(2).mean().sqrt())},
+                                 "greedy_frames_compared": int(n_cmp), "greedy_frames_until_first_fork": fork,
+                                 "greedy_token_agreement": float((greedy_b[..., :n_cmp] == greedy_f[..., :n_cmp]).float().mean())},
+                   "what": "weights of the decode step quantised once per model to e4m3 with one power-of-two scale per row (decode.cu: "
+                           "quant_e4m3_kernel); prefill, KV cache, activations, DAC unchanged; value = prefill + %d FP8 decode steps + DAC" % (N + 8)}
+        except Exception as e:                                   # the bf16 line must not depend on the opt-in mode
+            fp8 = {"error": repr(e)[:300]}
+        finally:
+            os.environ.pop("ZB_FP8", None)
+    del cond_dev
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         del w
@@ -480,7 +535,7 @@ def run_b200(args):
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": config_dict(args, n_gpus), "frames_per_second": head["frames_per_second"],
                 "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"], "roofline": roof,
-                "breakdown_ms": head["breakdown_ms"], "ttfa": ttfa, "batch64": batch64, "hybrid_batch1": hybrid, "reference_gpu_eager": ref_gpu,
+                "breakdown_ms": head["breakdown_ms"], "ttfa": ttfa, "batch64": batch64, "hybrid_batch1": hybrid, "fp8_batch1": fp8, "reference_gpu_eager": ref_gpu,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

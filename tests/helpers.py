@@ -70,3 +70,21 @@ def eos_boosted(weights: dict, boost: float) -> dict:
     hw[1024] = (boost * w["backbone.norm_f.bias"].float()).to(hw.dtype)
     w["fused_heads.weight"] = hw
     return w
+
+
+FP8_KEYS = ("mixer.in_proj.weight", "mixer.out_proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")
+
+
+def fp8_dequantised(weights: dict) -> dict:
+    """The decode matrices after the FP8 mode's quantiser (zonos_b200/csrc/decode.cu: quant_e4m3_kernel): e4m3 with one
+    power-of-two scale per weight row, the row's largest |w| / scale in [1, 2).  The dequantised value q * scale is exactly
+    a bf16 number, so the FP8 kernel can be compared with the bf16 kernel run on THESE weights."""
+    out = dict(weights)
+    for k, v in weights.items():
+        if k.endswith(FP8_KEYS) or k == "fused_heads.weight":
+            f = v.float()
+            amax = f.abs().amax(dim=1, keepdim=True)
+            _, e = torch.frexp(amax)                                        # amax = m * 2^e, m in [0.5, 1)
+            sc = torch.where(amax > 0, torch.ldexp(torch.ones_like(amax), e - 1), torch.ones_like(amax))
+            out[k] = ((f / sc).clamp(-1.875, 1.875).to(torch.float8_e4m3fn).float() * sc).to(v.dtype)   # never rounds up to 2.0: idempotent
+    return out

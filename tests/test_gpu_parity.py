@@ -306,6 +306,98 @@ def test_in_place_weight_update_reaches_the_derived_copies(monkeypatch):
     assert not torch.equal(first, second)
 
 
+def _compare_fp8_sessions(model, dims, B, Lc, N, monkeypatch, atol_scale):
+    """One model, the same call with ZB_FP8=0 and =1 (read per session): per-call logits while the sampled histories agree."""
+    cond = make_conditioning(2 * B, Lc, dims["d_model"], seed=4).to(DEV)
+    q = q_stream_from_seed(5, N + 9, B)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ZB_FP8", mode)
+        trace = {}
+        codes = model.generate(cond, max_new_tokens=N, batch_size=B, q_stream=q, trace=trace)
+        lg = trace["logits"]
+        out[mode] = (codes.cpu(), (torch.stack(list(lg)) if isinstance(lg, list) else lg).cpu(), trace["delayed"].cpu())
+    monkeypatch.setenv("ZB_FP8", "0")
+    (c0, l0, d0), (c1, l1, d1) = out["0"], out["1"]
+    assert torch.equal(l0[0], l1[0])                            # the prefill does not change with the mode
+    alive = torch.ones(B, dtype=torch.bool)
+    compared, worst = 0, 0.0
+    for call in range(1, min(l0.shape[0], l1.shape[0], d0.shape[-1] - 1)):
+        for b in range(B):
+            if alive[b]:
+                r = logits_close(l1[call, b], l0[call, b])
+                assert r <= atol_scale, (B, call, b, r)
+                worst = max(worst, r)
+                compared += 1
+        alive &= (d1[..., 1 + call] == d0[..., 1 + call]).all(dim=1)   # flat random-init heads: a near-tie forks an utterance
+    return compared, worst
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_fp8_mode_equals_bf16_kernel_on_dequantised_weights(B, monkeypatch):
+    """SURVEY 8(f) rank 1, opt-in (ZB_FP8=1): the persistent decode step on an e4m3 copy of its matrices (one power-of-two scale
+    per row, e4m3 pair -> f16x2 -> HFMA2, fp32 from the stage sum on).  The dequantised weights are exactly bf16 numbers, so
+    the SAME model loaded with them must give the same logits through the bf16 kernel (ZB_FP8=0) and through the FP8 kernel
+    (ZB_FP8=1, which re-quantises them to the identical bytes): only the short f16 product chains differ.  Tiny dims exercise
+    the K = 512 / 1024 stage geometries; launch counts prove the quantiser ran once and only in the FP8 sessions."""
+    from helpers import fp8_dequantised
+    w = fp8_dequantised(make_backbone_weights(**TINY_DIMS, seed=11))
+    model = build_b200_model(TINY_DIMS, w, DEV)
+    ctx = model._ctx()
+    cond = make_conditioning(2 * B, 10, TINY_DIMS["d_model"], seed=9).to(DEV)
+    q = q_stream_from_seed(3, 12 + 9, B)
+    monkeypatch.setenv("ZB_FP8", "0")
+    model.generate(cond, max_new_tokens=12, batch_size=B, q_stream=q)
+    n0 = ctx.launch_count()
+    plain = model.generate(cond, max_new_tokens=12, batch_size=B, q_stream=q)
+    n1 = ctx.launch_count()
+    monkeypatch.setenv("ZB_FP8", "1")
+    first = model.generate(cond, max_new_tokens=12, batch_size=B, q_stream=q)
+    n2 = ctx.launch_count()
+    second = model.generate(cond, max_new_tokens=12, batch_size=B, q_stream=q)
+    n3 = ctx.launch_count()
+    assert torch.equal(first, second)                           # fixed summation orders: bit-reproducible
+    assert (n2 - n1) - (n3 - n2) == 4 * TINY_DIMS["n_layer"] + 1, (n0, n1, n2, n3)     # one quantiser launch per matrix, once
+    assert n3 - n2 == n1 - n0 or plain.shape != first.shape
+    compared, worst = _compare_fp8_sessions(model, TINY_DIMS, B, 24, 24, monkeypatch, 1.0)
+    assert compared >= 3 * B, "the two modes parted ways before three steps could be compared"
+
+
+def test_fp8_mode_full_size(full_model, monkeypatch):
+    """Full size (D = 2048, F = 8192: the NC = 4 / RW = 2 geometry of fc2, 10-stage ring of 16 KB stages).  (a) On dequantised
+    weights the FP8 kernel must match the bf16 kernel like two bf16 kernels match each other (LOGIT_ATOL).  (b) On the ORIGINAL
+    weights the difference is the e4m3 quantisation itself: recorded, and bounded loosely (3 mantissa bits: ~2-3 % per weight,
+    random signs) - the tolerance contract of the mode, reported by bench.py as `fp8_batch1.tolerance`."""
+    from helpers import fp8_dequantised
+    model, w = full_model
+    model.load_state_dict(fp8_dequantised(w))
+    try:
+        compared, worst = _compare_fp8_sessions(model, TRANSFORMER_DIMS, 1, 40, 16, monkeypatch, 1.0)
+        assert compared >= 3
+    finally:
+        model.load_state_dict(w)
+    cond = make_conditioning(2, 40, TRANSFORMER_DIMS["d_model"], seed=4).to(DEV)
+    q = q_stream_from_seed(5, 4 + 9, 1)
+    lg = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ZB_FP8", mode)
+        trace = {}
+        model.generate(cond, max_new_tokens=4, batch_size=1, q_stream=q, trace=trace)
+        t_ = trace["logits"]
+        lg[mode] = (torch.stack(list(t_)) if isinstance(t_, list) else t_).cpu()
+    monkeypatch.setenv("ZB_FP8", "0")
+    assert torch.equal(lg["0"][0], lg["1"][0])
+    a, b = lg["1"][1, 0], lg["0"][1, 0]                         # first decode step: same history
+    fin = torch.isfinite(b)
+    assert torch.equal(torch.isfinite(a), fin)
+    err = (a[fin] - b[fin])
+    spread = (b[fin] - b[fin].mean()).pow(2).mean().sqrt()
+    rel = float(err.pow(2).mean().sqrt() / spread)
+    print(f"fp8 vs bf16, original weights, first decode step: rms err {float(err.pow(2).mean().sqrt()):.4f}, max {float(err.abs().max()):.4f}, "
+          f"logit spread {float(spread):.4f}, ratio {rel:.3f}")
+    assert 0.0 < rel < 0.5, rel                                 # not identical (the mode is on), not garbage
+
+
 def test_generate_tcgen05_eos_and_prefix_golden(monkeypatch):
     """The reference-recorded B=2 case with an audio prefix, EOS and the unified sampler, through decode_tc.cu."""
     monkeypatch.setenv("ZB_DECODE_TC", "2")

@@ -131,7 +131,7 @@ zb_status zb_model_create(zb_ctx* ctx, const zb_model_desc* desc, zb_model** out
 
 zb_status zb_model_destroy(zb_model* model) { delete model; return ZB_OK; }
 zb_status zb_model_weights_changed(zb_model* model) {
-  if (model) model->tcw_valid = false;                       // derived copies are rebuilt by the next generate session
+  if (model) model->tcw_valid = model->f8w_valid = false;   // derived copies are rebuilt by the next generate session
   return ZB_OK;
 }
 

@@ -10,6 +10,9 @@
 
 #include <algorithm>
 
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "tc.cuh"
 
 namespace {
@@ -97,6 +100,7 @@ struct GemvArgs {
   const zb_loop_state* loop; int T_delayed;
   int ring_stages, prefetch_ahead;      // gemv3: stages in the shared-memory ring, stages prefetched into L2 beyond it
   unsigned long long* timeline;         // debug: 8 globaltimer stamps per launch (CTA 0), or null
+  const float* wscale;                  // persistent kernel, FP8 mode: one power-of-two scale per weight row (W then holds e4m3 bytes)
 };
 
 
@@ -709,6 +713,7 @@ struct MegaLayer {
   // Mamba2 layers (kind 1): conv1d / SSM parameters, gated-norm weight, this layer's recurrent state of all rows
   const bf16 *conv_w, *conv_b, *dt_bias, *A_log, *Dp, *mnorm_w; bf16 *conv_state, *ssm_state; long long kind;
   const bf16 *in_t, *out_t, *fc1_t, *fc2_t;                   // the same matrices re-laid out for the tcgen05 consumer (see MegaTcGeo)
+  const float *s_in, *s_out, *s_fc1, *s_fc2;                  // FP8 mode: row scales (in_proj ... fc2 then point at e4m3 bytes, [N, K] row-major)
 };
 // tcgen05 consumer: a matrix [N, K] is cut into units of RB weight rows (a multiple of 8; fc1: RBv value rows followed by
 // the RBv gate rows of the same features), unit u belongs to CTA u.  K is cut into S segments of Ks = K / S elements and
@@ -738,6 +743,7 @@ struct MegaArgs {
   unsigned long long* steplog;    // debug: [2*step] start, [2*step+1] end of every step (CTA 0)
   // tcgen05 consumer (decode_step_kernel<R, true>)
   const bf16* heads_t; MegaTcGeo tg[TG_COUNT];
+  const float* s_heads;   // FP8 mode (decode_step_kernel<R, 2>): row scales of the heads (`heads` then points at e4m3 bytes)
   // hybrid stacks: Mamba2 layers run as three phases (in_proj, conv1d step + state update, gated norm + out_proj)
   int nph, d_inner, m_nheads, ipo, conv_dim; uint32_t *zxt, *ygt;
 };
@@ -805,12 +811,16 @@ __device__ __forceinline__ void mega_slice(const GemvArgs& a, int& u_begin, int&
   nrows = (u_end - u_begin) * (kPairs ? 2 : 1);
 }
 
-// producer: stream this CTA's slice of one matrix through the ring (global stage counter gst)
+// producer: stream this CTA's slice of one matrix through the ring (global stage counter gst).  wsz = bytes per weight
+// (2: bf16; 1: the e4m3 copy of the FP8 mode).  A stage always holds the same ROWS, so with 1-byte weights it is 16 KB
+// and the ring has twice the stages.
 template <int EPI>
 __device__ __forceinline__ void mega_produce(const GemvArgs& a, unsigned char* ring, uint64_t* full_bar, uint64_t* empty_bar, int S, int& gst,
-                                             uint64_t pol, int lane) {
+                                             uint64_t pol, int lane, int wsz = 2) {
   constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
-  const int K = a.K, row_bytes = K * 2, RPS = kMegaStageBytes / row_bytes;
+  const int K = a.K, row_bytes = K * wsz, RPS = kMegaStageBytes / (K * 2);
+  const uint32_t stage_bytes = (uint32_t)(RPS * row_bytes);   // == kMegaStageBytes for bf16, half of it for e4m3
+  const unsigned char* W8 = reinterpret_cast<const unsigned char*>(a.W);
   int u_begin, nrows;
   mega_slice<EPI>(a, u_begin, nrows);
   const int nstage = (nrows + RPS - 1) / RPS;
@@ -818,18 +828,18 @@ __device__ __forceinline__ void mega_produce(const GemvArgs& a, unsigned char* r
     const int slot = gst % S;
     if (gst >= S) mbar_wait(&empty_bar[slot], ((gst / S) - 1) & 1);
     const int r0 = st * RPS;
-    if (lane == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)kMegaStageBytes);
+    if (lane == 0) mbar_expect_tx(&full_bar[slot], stage_bytes);
     __syncwarp();
-    unsigned char* dst = ring + (size_t)slot * kMegaStageBytes;
+    unsigned char* dst = ring + (size_t)slot * stage_bytes;
     if (!kPairs && r0 + RPS <= nrows) {
       if (lane == 0) {
-        if (pol) bulk_g2s(dst, a.W + (size_t)(u_begin + r0) * K, (uint32_t)kMegaStageBytes, &full_bar[slot], pol);
-        else bulk_g2s_nohint(dst, a.W + (size_t)(u_begin + r0) * K, (uint32_t)kMegaStageBytes, &full_bar[slot]);
+        if (pol) bulk_g2s(dst, W8 + (size_t)(u_begin + r0) * row_bytes, stage_bytes, &full_bar[slot], pol);
+        else bulk_g2s_nohint(dst, W8 + (size_t)(u_begin + r0) * row_bytes, stage_bytes, &full_bar[slot]);
       }
     } else {
       for (int q = lane; q < RPS; q += 32) {
         const int lr = min(r0 + q, nrows - 1);
-        const bf16* src = a.W + (size_t)row_of_local<EPI>(a, u_begin, lr) * K;
+        const unsigned char* src = W8 + (size_t)row_of_local<EPI>(a, u_begin, lr) * row_bytes;
         if (pol) bulk_g2s(dst + (size_t)q * row_bytes, src, row_bytes, &full_bar[slot], pol);
         else bulk_g2s_nohint(dst + (size_t)q * row_bytes, src, row_bytes, &full_bar[slot]);
       }
@@ -837,8 +847,37 @@ __device__ __forceinline__ void mega_produce(const GemvArgs& a, unsigned char* r
   }
 }
 
+// ---- FP8 mode of the FFMA consumer (decode_step_kernel<R, 2>, opt-in: ZB_FP8=1) ---------------
+// Weights: e4m3 bytes [N, K] + one power-of-two fp32 scale per row with |w| / scale < 2, so that (a) the dequantised
+// weight q * scale is exactly a bf16 number - the FP8 kernel can be checked against the bf16 kernel run on the
+// dequantised weights - and (b) products stay far inside the f16 range.  An e4m3 pair becomes an f16x2 with ONE cvt
+// (exact) and meets the activation pair in HFMA2: 4 cvt + 4 R HFMA2 per 8 weights against 8 shifts + 4 R FFMA2 for
+// bf16 (converting e4m3 to fp32 would cost 12 and lose to the bf16 path per weight).  A lane's f16 chain is NC * 4
+// products long (8 or 16) before it is widened to fp32; stage sums, the K-slice reduction and the epilogue are fp32 as before.
+__device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint32_t pair16) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"((unsigned short)pair16));   // low byte -> low half
+  return r;
+}
+__device__ __forceinline__ void hfma2_acc(uint32_t& d, uint32_t a, uint32_t b) {
+  asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(d) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float sum_f16x2(uint32_t v) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return f.x + f.y;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+  return r;
+}
+
 // consumers: one matrix phase.  wait_full / release control the out_proj "hold" (first pass keeps the slots).
-template <int R, int NC, int RW, int PRO, int EPI>
+template <int R, int NC, int RW, int PRO, int EPI, bool F8 = false>
 __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* ring, float* part, uint64_t* full_bar, uint64_t* empty_bar,
                                              float (*red)[kMW][4], int S, int& gst, bool release, int warp, int lane,
                                              const uint32_t* xt, uint32_t tag_in, uint32_t* yt, uint32_t tag_out, const uint32_t* rt, uint32_t* qt,
@@ -847,7 +886,9 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
 #define DBG(i) do { if (dbg && threadIdx.x == 0) dbg[i] = gtime(); } while (0)
   constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
   constexpr int Kc = NC * 256;
-  const int K = a.K, row_bytes = K * 2;
+  constexpr int kWsz = F8 ? 1 : 2;                             // bytes per weight
+  constexpr uint32_t kStage = kMegaStageBytes / (F8 ? 2 : 1);  // a stage holds the same rows in both modes
+  const int K = a.K, row_bytes = K * kWsz;
   const int KS = K / Kc;
   const int RPS = (kMW / KS) * RW;
   int u_begin, nrows;
@@ -950,11 +991,15 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
     }
   }
   DBG(4);
-  unsigned long long x2[R][NC * 4];
+  unsigned long long x2[F8 ? 1 : R][F8 ? 1 : NC * 4];
+  uint32_t xh[F8 ? R : 1][F8 ? NC * 4 : 1];                   // FP8 mode: the activation pairs as f16x2
 #pragma unroll
   for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int e = 0; e < NC * 4; ++e) x2[i][e] = pack_f32x2(xf[i][2 * e], xf[i][2 * e + 1]);
+    for (int e = 0; e < NC * 4; ++e) {
+      if (F8) xh[F8 ? i : 0][F8 ? e : 0] = pack_f16x2_sat(xf[i][2 * e], xf[i][2 * e + 1]);
+      else x2[F8 ? 0 : i][F8 ? 0 : e] = pack_f32x2(xf[i][2 * e], xf[i][2 * e + 1]);
+    }
 
   // ---- operands of this thread's epilogue (residual value, RoPE cos/sin, KV page): fetched NOW so their L2 round
   // trips overlap the weight streaming instead of trailing it ----
@@ -969,6 +1014,8 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   float pre_resid = 0.f;
   float2 pre_cs = make_float2(1.f, 0.f);
   int pre_pos = 0, pre_page = 0;
+  float wsc0 = 1.f, wsc1 = 1.f;                                // FP8 mode: scales of this item's weight rows
+  if (F8 && e_on) { wsc0 = __ldg(a.wscale + en0); if (kPairs) wsc1 = __ldg(a.wscale + en1); }
   if (e_on) {
     if (EPI == EPI_RESID) pre_resid = untag(ld_relaxed_u32(rt + (size_t)ei * a.ldr + en0));   // validated by this CTA in an earlier phase
     if (EPI == EPI_QKV && qkv_pre && qkv_pre->valid) {
@@ -988,43 +1035,67 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   const int my_idx = multi_reduce_index<V>(lane);
   const bool writer = (lane & ((32 / V) - 1)) == 0;
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-  const uint32_t lane_base = smem_u32(ring) + (uint32_t)(rg * RW) * row_bytes + (uint32_t)(koff + lane * 8) * 2;
+  const uint32_t lane_base = smem_u32(ring) + (uint32_t)(rg * RW) * row_bytes + (uint32_t)(koff + lane * 8) * kWsz;
   const uint32_t part_lane = smem_u32(part) + (uint32_t)((((rg * RW + my_idx / R) * KS + ks) * R + my_idx % R) * 4);
   const uint32_t part_stage = (uint32_t)(RPS * KS * R * 4);
   uint32_t slot = (uint32_t)(gst % S), phase = (uint32_t)((gst / S) & 1);   // advanced incrementally: no division per stage
-  uint32_t src = lane_base + slot * kMegaStageBytes, fb = full0 + slot * 8, eb = empty0 + slot * 8;
+  uint32_t src = lane_base + slot * kStage, fb = full0 + slot * 8, eb = empty0 + slot * 8;
   uint32_t part_dst = part_lane;
   gst += nstage;
   for (int st = 0; st < nstage; ++st) {
     mbar_wait_u32(fb, phase);
     if (st == 0) DBG(5);
-    unsigned long long acc2[V];
+    float acc[V];
+    if (F8) {
+      uint32_t acch[V];
 #pragma unroll
-    for (int q = 0; q < V; ++q) acc2[q] = 0ull;
+      for (int q = 0; q < V; ++q) acch[q] = 0u;
 #pragma unroll
-    for (int w = 0; w < RW; ++w) {
+      for (int w = 0; w < RW; ++w) {
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const uint4 wv = lds128(src + w * row_bytes + c * 512);
-        const uint32_t c0[4] = {wv.x, wv.y, wv.z, wv.w};
+        for (int c = 0; c < NC; ++c) {
+          const uint2 wv = lds64(src + w * row_bytes + c * 256);    // this lane's 8 weights of chunk c: k = koff + 256 c + 8 lane ...
+          const uint32_t c0[2] = {wv.x, wv.y};
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const unsigned long long w2 = pack_f32x2(bf16lo(c0[jj]), bf16hi(c0[jj]));
+          for (int jj = 0; jj < 4; ++jj) {                           // pair jj = weights (2 jj, 2 jj + 1) = one half of c0[jj / 2]
+            const uint32_t w2 = e4m3x2_to_f16x2(c0[jj >> 1] >> ((jj & 1) * 16));
 #pragma unroll
-          for (int i = 0; i < R; ++i) ffma2(acc2[w * R + i], w2, x2[i][c * 4 + jj]);
+            for (int i = 0; i < R; ++i) hfma2_acc(acch[w * R + i], w2, xh[F8 ? i : 0][F8 ? c * 4 + jj : 0]);
+          }
         }
       }
-    }
-    __syncwarp();
-    if (release && lane == 0) mbar_arrive_u32(eb);
-    float acc[V];
+      __syncwarp();
+      if (release && lane == 0) mbar_arrive_u32(eb);
 #pragma unroll
-    for (int q = 0; q < V; ++q) acc[q] = sum_f32x2(acc2[q]);
+      for (int q = 0; q < V; ++q) acc[q] = sum_f16x2(acch[q]);
+    } else {
+      unsigned long long acc2[V];
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc2[q] = 0ull;
+#pragma unroll
+      for (int w = 0; w < RW; ++w) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint4 wv = lds128(src + w * row_bytes + c * 512);
+          const uint32_t c0[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const unsigned long long w2 = pack_f32x2(bf16lo(c0[jj]), bf16hi(c0[jj]));
+#pragma unroll
+            for (int i = 0; i < R; ++i) ffma2(acc2[w * R + i], w2, x2[F8 ? 0 : i][F8 ? 0 : c * 4 + jj]);
+          }
+        }
+      }
+      __syncwarp();
+      if (release && lane == 0) mbar_arrive_u32(eb);
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] = sum_f32x2(acc2[q]);
+    }
     warp_reduce_multi<V>(acc);
     if (writer) sts32(part_dst, acc[0]);
     part_dst += part_stage;
     if (++slot == (uint32_t)S) { slot = 0; phase ^= 1u; src = lane_base; fb = full0; eb = empty0; }
-    else { src += kMegaStageBytes; fb += 8; eb += 8; }
+    else { src += kStage; fb += 8; eb += 8; }
   }
   DBG(6);
   asm volatile("bar.sync 1, %0;" ::"n"(kMW * 32) : "memory");
@@ -1040,6 +1111,7 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
       const float* s0 = part + (size_t)ej * KS * R;
       for (int q = 0; q < KS; ++q) { v0 += s0[q * R + ei]; if (cfg) u0 += s0[q * R + a.B + ei]; }
     }
+    if (F8) { v0 *= wsc0; v1 *= wsc1; u0 *= wsc0; }           // power-of-two row scales: exact
     if (EPI == EPI_RESID) {
       st_relaxed_u32(yt + (size_t)ei * a.ldy + en0, tag_word(pre_resid + rbf(v0), tag_out));
     } else if (EPI == EPI_STORE) {
@@ -1666,8 +1738,12 @@ __device__ __forceinline__ void mega_fill(GemvArgs& a, const MegaArgs& m, int R)
   a.page_table = m.page_table; a.max_pages = m.max_pages; a.F = m.F; a.B = m.B; a.cfg_scale = m.cfg_scale; a.logits = m.logits; a.QV = m.QV;
 }
 
-template <int R, bool TC>
+// MODE 0: FFMA2 consumer on the caller's bf16 weights (default); 1: tcgen05 consumer on the tile-ordered copy (ZB_MEGA_TC=1);
+// 2: FP8 mode - the FFMA consumer on the e4m3 copy (ZB_FP8=1, transformer stacks only)
+template <int R, int MODE>
 __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __grid_constant__ MegaArgs m) {
+  constexpr bool TC = MODE == 1, F8 = MODE == 2;
+  constexpr int kStage = kMegaStageBytes / (F8 ? 2 : 1), kWsz = F8 ? 1 : 2;
   extern __shared__ __align__(128) unsigned char smem_m[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tc_bar[2];
   __shared__ float red[2][kMW][4];
@@ -1677,7 +1753,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
   const int S = m.ring_stages;
   // TC: the ring holds UMMA tiles (1024-byte aligned swizzle atoms), followed by the 32 KB activation image
   unsigned char* ring = TC ? reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_m) + 1023) & ~(uintptr_t)1023) : smem_m;
-  unsigned char* abuf = ring + (size_t)S * kMegaStageBytes;
+  unsigned char* abuf = ring + (size_t)S * kStage;
   float* part = reinterpret_cast<float*>(abuf + (TC ? kMegaTcImageBytes : 0));
   unsigned char* attn_scratch = reinterpret_cast<unsigned char*>(part) + m.part_bytes;
   bf16* nbuf = reinterpret_cast<bf16*>(attn_scratch + kMegaAttnBytes);   // [2 buffers][weight | bias][D]: norm parameters, copied a layer ahead
@@ -1722,13 +1798,13 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       }
       mega_fill(a, m, R);
       a.W = L.in_proj; a.N = nqkv; a.K = m.D;
-      mega_produce<EPI_QKV>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+      mega_produce<EPI_QKV>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
       a.W = L.out_proj; a.N = m.D; a.K = qn;
-      mega_produce<EPI_STORE>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+      mega_produce<EPI_STORE>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
       a.W = L.fc1; a.N = 2 * m.F; a.K = m.D;
-      mega_produce<EPI_SILU>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+      mega_produce<EPI_SILU>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
       a.W = L.fc2; a.N = m.D; a.K = m.F;
-      mega_produce<EPI_RESID>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+      mega_produce<EPI_RESID>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
     }
     if (TC) {
       mega_produce_tc(m.heads_t, m.tg[TG_HEADS], m.D, ring, full_bar, empty_bar, S, gst, pol, lane);
@@ -1736,7 +1812,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     }
     mega_fill(a, m, R);
     a.W = m.heads; a.N = m.QV; a.K = m.D;
-    mega_produce<EPI_HEADS>(a, ring, full_bar, empty_bar, S, gst, pol, lane);
+    mega_produce<EPI_HEADS>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
     return;
   }
 
@@ -1826,7 +1902,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       mega_scan_prefetch(m, L, has_unit ? (int)blockIdx.x : -1, attn_scratch);
       {
         unsigned long long* slot = MEGA_STAMP_SLOT();
-        mega_consume<R, 2, 4, PRO_NORM, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.zxt, TAG(ph),
+        mega_consume<R, 2, 4, PRO_NORM, EPI_STORE, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.zxt, TAG(ph),
                                                    nullptr, nullptr, nullptr, slot, 1);
       }
       MEGA_STAMP(); ++ph;
@@ -1843,7 +1919,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       a.W = L.out_proj; a.N = m.D; a.K = m.d_inner; a.ldx = 2 * m.d_inner; a.ldy = m.D; a.ldr = m.D; a.nw = nbuf + 2 * m.D; a.nb = nullptr;
       {
         unsigned long long* slot = MEGA_STAMP_SLOT();
-        mega_consume<R, 2, 4, PRO_GATED, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ygt, TAG(ph - 1), m.xt, TAG(ph),
+        mega_consume<R, 2, 4, PRO_GATED, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ygt, TAG(ph - 1), m.xt, TAG(ph),
                                                     m.xt, nullptr, nullptr, slot, 1, nullptr, nullptr, m.ygt + m.d_inner, 2 * m.d_inner, TAG(ph - 1));
       }
       MEGA_STAMP(); ++ph;
@@ -1853,6 +1929,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     // A: norm -> in_proj -> RoPE -> KV append (+ q)
     mega_fill(a, m, R);
     a.W = L.in_proj; a.N = nqkv; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = L.norm_b ? nbuf + m.D : nullptr; a.kv_layer = L.kv_layer;
+    a.wscale = L.s_in;
     mega_attention_prefetch(m, L.kv_layer, ameta, attn_scratch);
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
@@ -1860,7 +1937,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
         mega_consume_tc<R, 1, PRO_NORM, EPI_QKV>(a, m.tg[TG_QKV], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
                                                  nullptr, TAG(ph), nullptr, 0u, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
       else
-      mega_consume<R, 2, 4, PRO_NORM, EPI_QKV>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
+      mega_consume<R, 2, 4, PRO_NORM, EPI_QKV, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
                                                nullptr, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
     }
     const int ph_in = ph;                                      // x was last written by phase ph_in - 1 (embedding or the previous fc2)
@@ -1882,7 +1959,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       for (int rep = 0; rep < m.out_proj_repeats; ++rep) {
         const bool last = rep == m.out_proj_repeats - 1;
         mega_fill(a, m, R);
-        a.W = L.out_proj; a.N = m.D; a.K = qn; a.ldx = qn; a.ldy = m.D; a.ldr = m.D;
+        a.W = L.out_proj; a.N = m.D; a.K = qn; a.ldx = qn; a.ldy = m.D; a.ldr = m.D; a.wscale = L.s_out;
         int g2 = gst0;
         unsigned long long* slot = MEGA_STAMP_SLOT();
         if (last) {
@@ -1891,7 +1968,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
                                                        TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph_in - 1), nullptr, nullptr, slot, 0, nullptr,
                                                        (stamping && li == 1) ? m.timeline + 208 : nullptr);
           else
-          mega_consume<R, 2, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane, src, TAG(ph - 1), m.xt, TAG(ph),
+          mega_consume<R, 2, 4, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane, src, TAG(ph - 1), m.xt, TAG(ph),
                                                      m.xt, nullptr, nullptr, slot);
         } else {
           uint32_t* dst = (src == m.y1t) ? m.ayt : m.y1t;
@@ -1899,7 +1976,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
             mega_consume_tc<R, 1, PRO_NONE, EPI_STORE>(a, m.tg[TG_OUT], ring, part, full_bar, empty_bar, ts, red, S, g2, false, warp, lane, src,
                                                        TAG(ph - 1), dst, TAG(ph), nullptr, 0u, nullptr, nullptr, slot, 0, nullptr);
           else
-          mega_consume<R, 2, 4, PRO_NONE, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, g2, false, warp, lane, src, TAG(ph - 1), dst, TAG(ph),
+          mega_consume<R, 2, 4, PRO_NONE, EPI_STORE, F8>(a, ring, part, full_bar, empty_bar, red, S, g2, false, warp, lane, src, TAG(ph - 1), dst, TAG(ph),
                                                      nullptr, nullptr, nullptr, slot);
           src = dst;
         }
@@ -1910,20 +1987,21 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     // E: norm2 -> fc1 -> value * silu(gate)
     mega_fill(a, m, R);
     a.W = L.fc1; a.N = 2 * m.F; a.K = m.D; a.ldx = m.D; a.nw = nbuf + 2 * m.D; a.nb = L.norm2_b ? nbuf + 3 * m.D : nullptr; a.ldy = m.F;
+    a.wscale = L.s_fc1;
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       if (TC)
         mega_consume_tc<R, 1, PRO_NORM, EPI_SILU>(a, m.tg[TG_FC1], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
                                                   m.ht, TAG(ph), nullptr, 0u, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 216 : nullptr);
       else
-      mega_consume<R, 2, 4, PRO_NORM, EPI_SILU>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
+      mega_consume<R, 2, 4, PRO_NORM, EPI_SILU, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
                                                 nullptr, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 220 : nullptr);
     }
     MEGA_STAMP(); ++ph;
     if (!lastl) norm_prefetch(1, nx1w, nx1b);
     // F: fc2 + residual
     mega_fill(a, m, R);
-    a.W = L.fc2; a.N = m.D; a.K = m.F; a.ldx = m.F; a.ldy = m.D; a.ldr = m.D;
+    a.W = L.fc2; a.N = m.D; a.K = m.F; a.ldx = m.F; a.ldy = m.D; a.ldr = m.D; a.wscale = L.s_fc2;
     {
       unsigned long long* slot = MEGA_STAMP_SLOT();
       if (TC) {
@@ -1936,24 +2014,24 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
           mega_consume_tc<R, 1, PRO_NONE, EPI_RESID>(a, m.tg[TG_FC2], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.ht,
                                                      TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph - 2), nullptr, nullptr, slot, 0, nullptr);
       } else if (m.F == 8192)
-        mega_consume<R, 4, 2, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
+        mega_consume<R, 4, 2, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
                                                    m.xt, nullptr, nullptr, slot);
       else
-        mega_consume<R, 2, 4, PRO_NONE, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
+        mega_consume<R, 2, 4, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
                                                    m.xt, nullptr, nullptr, slot);
     }
     MEGA_STAMP(); ++ph;
   }
   // heads: final norm -> fused heads -> fp32 -> CFG mix
   mega_fill(a, m, R);
-  a.W = m.heads; a.N = m.QV; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = m.normf_b ? nbuf + m.D : nullptr;
+  a.W = m.heads; a.N = m.QV; a.K = m.D; a.ldx = m.D; a.nw = nbuf; a.nb = m.normf_b ? nbuf + m.D : nullptr; a.wscale = m.s_heads;
   {
     unsigned long long* slot = MEGA_STAMP_SLOT();
     if (TC)
       mega_consume_tc<R, 1, PRO_NORM, EPI_HEADS>(a, m.tg[TG_HEADS], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
                                                  nullptr, 0u, nullptr, 0u, nullptr, nullptr, slot, 0, nullptr);
     else
-    mega_consume<R, 2, 4, PRO_NORM, EPI_HEADS>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, 0u,
+    mega_consume<R, 2, 4, PRO_NORM, EPI_HEADS, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, 0u,
                                                nullptr, nullptr, nullptr, slot);
   }
   MEGA_STAMP();
@@ -2144,6 +2222,29 @@ __global__ void __launch_bounds__(256) gated_norm_kernel(GNormArgs a) {
 
 // ------------------------------------------------------------------ host side ----------------
 // ---- tile-ordered weight copy for the tcgen05 consumer of the persistent kernel (MegaTcGeo) -------------------------
+// FP8 mode: one weight row per CTA -> e4m3 bytes + a power-of-two scale with |w| / scale in [1, 2) for the row's largest
+// element (so q * scale is exactly a bf16 number, and e4m3's 3 mantissa bits are all the rounding there is)
+__global__ void __launch_bounds__(256) quant_e4m3_kernel(const bf16* W, unsigned char* q, float* scale, int K) {
+  __shared__ float red[8];
+  const bf16* w = W + (size_t)blockIdx.x * K;
+  float amax = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) amax = fmaxf(amax, fabsf(bf2f(w[k])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+  const float sc = (amax > 0.f && amax < 3.0e38f) ? ldexpf(1.0f, ilogbf(amax)) : 1.0f;
+  unsigned char* dst = q + (size_t)blockIdx.x * K;
+  // |w| / sc < 2; a value that would round UP to 2.0 is held at 1.875 (the largest e4m3 number below 2), so that quantising the
+  // dequantised row finds the same scale and reproduces the same bytes (the quantiser is idempotent)
+  for (int k = threadIdx.x; k < K; k += 256)
+    dst[k] = (unsigned char)__nv_cvt_float_to_fp8(fminf(fmaxf(bf2f(w[k]) / sc, -1.875f), 1.875f), __NV_SATFINITE, __NV_E4M3);
+  if (threadIdx.x == 0) scale[blockIdx.x] = sc;
+}
+
 struct PretileArgs { const bf16* W; uint4* out; int N, K, RB, RBv, F, nunits, S; };
 // one thread per 16-byte chunk of the output; physical chunk c of tile row n holds logical chunk c ^ (n % 8) (128-byte swizzle)
 __global__ void __launch_bounds__(256) pretile_kernel(PretileArgs a) {
@@ -2605,11 +2706,70 @@ static zb_status mega_tc_pretile(zb_ctx* ctx, const zb_model* model, const MegaT
   return ZB_OK;
 }
 
+// ---- FP8 mode (opt-in, ZB_FP8=1): e4m3 copy of the decode matrices, [layer][in_proj | out_proj | fc1 | fc2][heads][scales] ----
+struct MegaF8Plan {
+  size_t off[4], layer_bytes, heads_off, scales_off;          // bytes
+  size_t soff[4], layer_scales, heads_soff;                   // floats, relative to scales_off
+  size_t total;
+  int N[4], K[4];
+};
+static MegaF8Plan mega_f8_plan(const zb_model_desc& d) {
+  MegaF8Plan p;
+  const int qn = d.n_heads * d.head_dim, nqkv = (d.n_heads + 2 * d.n_heads_kv) * d.head_dim;
+  const int N[4] = {nqkv, d.d_model, 2 * d.d_ff, d.d_model}, K[4] = {d.d_model, qn, d.d_model, d.d_ff};
+  size_t b = 0, f = 0;
+  for (int i = 0; i < 4; ++i) { p.N[i] = N[i]; p.K[i] = K[i]; p.off[i] = b; p.soff[i] = f; b += (size_t)N[i] * K[i]; f += (size_t)N[i]; }
+  p.layer_bytes = b; p.layer_scales = f;
+  p.heads_off = (size_t)d.n_layer * b;
+  const size_t hb = (size_t)d.n_codebooks * d.head_vocab * d.d_model;
+  p.scales_off = (p.heads_off + hb + 255) / 256 * 256;
+  p.heads_soff = (size_t)d.n_layer * f;
+  p.total = p.scales_off + (p.heads_soff + (size_t)d.n_codebooks * d.head_vocab) * sizeof(float);
+  return p;
+}
+// Read per session (tests compare both modes in one process).  Transformer stacks only: the Mamba2 phases keep bf16 weights.
+bool zb_mega_fp8_enabled(const zb_model* model, int R) {
+  return env_int("ZB_FP8", 0) && model->n_mamba == 0 && model->d.heads && !zb_mega_tc_enabled(model, R);
+}
+static zb_status mega_f8_build(zb_ctx* ctx, const zb_model* model, const MegaF8Plan& p, cudaStream_t stream) {
+  const zb_model_desc& d = model->d;
+  if (model->f8w && model->f8w_bytes < p.total) {
+    ZB_CUDA(ctx, cudaDeviceSynchronize());
+    ZB_CUDA(ctx, cudaFree(model->f8w));
+    model->f8w = nullptr; model->f8w_valid = false;
+  }
+  if (!model->f8w) {
+    ZB_CUDA(ctx, cudaMalloc(&model->f8w, p.total));
+    model->f8w_bytes = p.total; model->f8w_valid = false;
+  }
+  if (model->f8w_valid) return ZB_OK;
+  unsigned char* base = (unsigned char*)model->f8w;
+  float* scales = (float*)(base + p.scales_off);
+  auto run = [&](const void* W, size_t off, size_t soff, int N, int K) -> zb_status {
+    quant_e4m3_kernel<<<N, 256, 0, stream>>>((const bf16*)W, base + off, scales + soff, K);
+    ZB_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return ZB_OK;
+  };
+  for (int li = 0; li < d.n_layer; ++li) {
+    const zb_layer& L = model->layers[li];
+    const void* W[4] = {L.in_proj, L.out_proj, L.fc1, L.fc2};
+    for (int i = 0; i < 4; ++i)
+      if (zb_status st = run(W[i], (size_t)li * p.layer_bytes + p.off[i], (size_t)li * p.layer_scales + p.soff[i], p.N[i], p.K[i])) return st;
+  }
+  if (zb_status st = run(d.heads, p.heads_off, p.heads_soff, d.n_codebooks * d.head_vocab, d.d_model)) return st;
+  model->f8w_valid = true;
+  return ZB_OK;
+}
+
 zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cache* cache, void* host_buf, cudaStream_t stream) {
   const zb_model_desc& d = model->d;
   MegaTcPlan tp;
   const bool tc = model->n_mamba == 0 && mega_tc_plan(d, ctx->num_sms, 2, &tp) && zb_mega_tc_enabled(model, 2) && d.heads;
   if (tc) { if (zb_status st = mega_tc_pretile(ctx, model, tp, stream)) return st; }
+  const bool f8 = !tc && zb_mega_fp8_enabled(model, 2);
+  const MegaF8Plan fp = mega_f8_plan(d);
+  if (f8) { if (zb_status st = mega_f8_build(ctx, model, fp, stream)) return st; }
   const size_t page_elems = (size_t)2 * d.n_heads_kv * ZB_PAGE_TOKENS * d.head_dim;
   MegaLayer* out = (MegaLayer*)host_buf;
   static const int share = env_int("ZB_DEBUG_SHARE_LAYERS", 0);   // debug: every layer streams layer 0's weights (L2-resident experiment)
@@ -2637,6 +2797,13 @@ zb_status zb_mega_layers_build(zb_ctx* ctx, const zb_model* model, const zb_cach
       const char* base = (const char*)model->tcw + (size_t)li * tp.layer_bytes;
       out[li].in_t = (const bf16*)(base + tp.off[TG_QKV]); out[li].out_t = (const bf16*)(base + tp.off[TG_OUT]);
       out[li].fc1_t = (const bf16*)(base + tp.off[TG_FC1]); out[li].fc2_t = (const bf16*)(base + tp.off[TG_FC2]);
+    }
+    if (f8) {                                                 // the weight pointers of this session's table are the e4m3 copy
+      const char* base = (const char*)model->f8w + (size_t)(share ? 0 : li) * fp.layer_bytes;
+      const float* sc = (const float*)((const char*)model->f8w + fp.scales_off) + (size_t)(share ? 0 : li) * fp.layer_scales;
+      out[li].in_proj = (const bf16*)(base + fp.off[0]); out[li].out_proj = (const bf16*)(base + fp.off[1]);
+      out[li].fc1 = (const bf16*)(base + fp.off[2]); out[li].fc2 = (const bf16*)(base + fp.off[3]);
+      out[li].s_in = sc + fp.soff[0]; out[li].s_out = sc + fp.soff[1]; out[li].s_fc1 = sc + fp.soff[2]; out[li].s_fc2 = sc + fp.soff[3];
     }
   }
   return ZB_OK;
@@ -2729,15 +2896,23 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     m.heads_t = (const bf16*)((const char*)model->tcw + tp.off[TG_HEADS]);
     pb = kMegaTcPartBytes;
   }
+  // FP8 mode: the session's layer table (zb_mega_layers_build) points at the e4m3 copy; a stage holds the same rows in 16 KB
+  const bool f8 = !tc && zb_mega_fp8_enabled(model, R) && model->f8w && model->f8w_valid;
+  if (f8) {
+    const MegaF8Plan fp = mega_f8_plan(d);
+    m.heads = (const bf16*)((const char*)model->f8w + fp.heads_off);
+    m.s_heads = (const float*)((const char*)model->f8w + fp.scales_off) + fp.heads_soff;
+  }
+  const size_t stage_bytes = f8 ? kMegaStageBytes / 2 : kMegaStageBytes;
   const size_t attn_bytes = kMegaAttnBytes + (size_t)4 * d.d_model * sizeof(bf16);   // attention tiles + two norm-parameter buffers
   const size_t avail = 227 * 1024 - 2048 - (tc ? kMegaTcImageBytes + 1024 : 0);      // (tc: activation image, 1024-byte alignment of the ring)
-  int stages = (int)((avail - pb - attn_bytes) / kMegaStageBytes);
+  int stages = (int)((avail - pb - attn_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   ZB_REQUIRE(ctx, stages >= 3, "persistent decode: not enough shared memory for the ring");
   m.ring_stages = stages; m.part_bytes = (int)pb;
   static const int evict_first = env_int("ZB_MEGA_EVICT_FIRST", 1);
   m.evict_first = evict_first;
-  const size_t smem = (size_t)stages * kMegaStageBytes + pb + attn_bytes + (tc ? kMegaTcImageBytes + 1024 : 0);
+  const size_t smem = (size_t)stages * stage_bytes + pb + attn_bytes + (tc ? kMegaTcImageBytes + 1024 : 0);
   auto launch = [&](auto kernel) -> zb_status {
     ZB_CUDA(ctx, zb_ensure_smem(ctx, kernel, smem));
     cudaLaunchConfig_t cfg = {};
@@ -2751,10 +2926,11 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     return ZB_OK;
   };
   if (env_int("ZB_MEGA_VERBOSE", 0) && loop && ctx->launches % 64 == 0)
-    fprintf(stderr, "[zb] persistent decode step: %s consumer, %d stages, smem %zu\n", tc ? "tcgen05" : "FFMA2", stages, smem);
-  if (tc) return R <= 2 ? launch(decode_step_kernel<2, true>) : launch(decode_step_kernel<4, true>);
-  if (R <= 2) return launch(decode_step_kernel<2, false>);
-  return launch(decode_step_kernel<4, false>);
+    fprintf(stderr, "[zb] persistent decode step: %s consumer, %d stages, smem %zu\n", tc ? "tcgen05" : f8 ? "FP8 (e4m3 -> HFMA2)" : "FFMA2", stages, smem);
+  if (tc) return R <= 2 ? launch(decode_step_kernel<2, 1>) : launch(decode_step_kernel<4, 1>);
+  if (f8) return R <= 2 ? launch(decode_step_kernel<2, 2>) : launch(decode_step_kernel<4, 2>);
+  if (R <= 2) return launch(decode_step_kernel<2, 0>);
+  return launch(decode_step_kernel<4, 0>);
 }
 
 // ---- diagnostics: launch ONE production kernel on scratch activations (bench.py roofline leg) ----

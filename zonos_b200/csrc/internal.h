@@ -30,7 +30,15 @@ struct zb_model {
   // Weight copy in the tile order of the persistent kernel's tcgen05 consumer (decode.cu, MegaTcGeo): built by the first
   // generate session that takes that path, rebuilt after zb_model_weights_changed(); owned by the model.
   mutable void* tcw = nullptr; mutable size_t tcw_bytes = 0; mutable int tcw_grid = 0; mutable bool tcw_valid = false;
-  ~zb_model() { if (tcw) { cudaSetDevice(ctx->device); cudaFree(tcw); } }
+  // FP8 (e4m3, one power-of-two scale per weight row) copy of the decode matrices for the persistent kernel's opt-in FP8 mode
+  // (decode.cu, ZB_FP8=1): [layer][in_proj | out_proj | fc1 | fc2 bytes] [heads bytes] [row scales, fp32].
+  // Built by the first generate session that asks for it, rebuilt after zb_model_weights_changed(); owned by the model.
+  mutable void* f8w = nullptr; mutable size_t f8w_bytes = 0; mutable bool f8w_valid = false;
+  ~zb_model() {
+    if (tcw || f8w) cudaSetDevice(ctx->device);
+    if (tcw) cudaFree(tcw);
+    if (f8w) cudaFree(f8w);
+  }
 };
 
 struct zb_sample_launch {

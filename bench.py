@@ -540,13 +540,15 @@ def run_b200(args):
                 return {"rows": r_[4], "logit_rms_err": (r_[0] / max(1, r_[2])) ** 0.5, "logit_max_abs_err": r_[1], "rms_of_bf16_logits": (r_[6] / max(1, r_[2])) ** 0.5,
                         "argmax_agreement": r_[3] / max(1, r_[4]), "mean_kl_bf16_to_fp8": r_[5] / max(1, r_[4])}
             wq_bytes = spec0["w_bytes"] // 2
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            fp8_traffic = json.load(open(tpath)).get("fp8_batch1_decode_step_dram_bytes_per_launch") if os.path.exists(tpath) else None
             mean_s = Lc + 1 + (n_small + N + 16) / 2
             step_bytes = wq_bytes + 2 * mean_s * spec0["kv_tok"] + 2 * spec0["kv_tok"] + 9 * spec0["d_model"] * 2 + 9 * 1025 * 4
             fp8 = {"value": (N / FRAME_RATE) / (t_full / 1e3 + head["breakdown_ms"]["dac_ms"] / 1e3), "unit": UNIT,
                    "us_per_decode_step": step_ms * 1e3, "speedup_of_the_step_vs_bf16": head["roofline"]["us_per_launch"] / (step_ms * 1e3),
                    "roofline": {"bound": "hbm", "kernel": "decode_step_kernel<R=2, FP8 mode> (e4m3 weights, HFMA2 consumer) + sample kernel",
                                 "algorithmic_bytes_per_launch": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": peak,
-                                "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
+                                "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "traffic": fp8_traffic},
                    "tolerance": {"how": "logits of the two modes on identical histories (same prefill: %s)" % prefill_same,
                                  "same_seeded_draws_%d_frames" % n_tol: dict(figures(ra), decode_calls_until_the_histories_fork=same_hist - 1),
                                  "first_decode_step_16_conditionings": figures(rb_)},

@@ -185,3 +185,34 @@ def test_from_local_reads_a_reference_format_checkpoint(tmp_path):
     for k, v in w.items():
         if k.startswith("backbone."):
             assert torch.equal(sd[k], v), k
+
+
+def test_fp8_quantiser_contract_on_the_host():
+    """The host restatement of the FP8 mode's quantiser (tests/helpers.py: fp8_dequantised = decode.cu: quant_e4m3_kernel):
+    every dequantised weight is exactly a bf16 number, is within e4m3's half-ulp (1/16 relative) of the original where the
+    original is a normal e4m3 multiple of its row scale, and quantising the dequantised weights changes nothing - the property
+    the GPU test relies on when it runs the bf16 kernel and the FP8 kernel on the same dequantised weights."""
+    from helpers import FP8_KEYS, fp8_dequantised
+    from zonos_b200.synthetic import TINY_DIMS, make_backbone_weights
+    w = make_backbone_weights(**TINY_DIMS, seed=11)
+    w["fused_heads.weight"][3] = 0                            # an all-zero row keeps scale 1 and stays zero
+    d1 = fp8_dequantised(w)
+    d2 = fp8_dequantised(d1)
+    touched = 0
+    for k, v in w.items():
+        if not (k.endswith(FP8_KEYS) or k == "fused_heads.weight"):
+            assert d1[k] is v
+            continue
+        touched += 1
+        a, b = v.float(), d1[k].float()
+        assert d1[k].dtype == v.dtype and torch.equal(b, b.bfloat16().float())
+        assert torch.equal(d1[k], d2[k]), k
+        amax = a.abs().amax(dim=1, keepdim=True)
+        big = a.abs() >= amax / 64                            # normal e4m3 range of the row (scale <= amax < 2 scale, normals from scale / 64)
+        rel = ((a - b).abs() / a.abs().clamp_min(1e-30))[big]
+        assert float(rel.max()) <= 1 / 16 + 1e-6, (k, float(rel.max()))
+        assert float((a - b).abs().max()) <= float(amax.max()) / 16
+        # 8 distinct magnitudes per binade, sign kept
+        assert torch.equal(torch.sign(b)[big], torch.sign(a)[big])
+    assert touched == 4 * TINY_DIMS["n_layer"] + 1
+    assert float(d1["fused_heads.weight"][3].abs().max()) == 0.0

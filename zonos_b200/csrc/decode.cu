@@ -812,14 +812,15 @@ __device__ __forceinline__ void mega_slice(const GemvArgs& a, int& u_begin, int&
 }
 
 // producer: stream this CTA's slice of one matrix through the ring (global stage counter gst).  wsz = bytes per weight
-// (2: bf16; 1: the e4m3 copy of the FP8 mode).  A stage always holds the same ROWS, so with 1-byte weights it is 16 KB
-// and the ring has twice the stages.
+// (2: bf16; 1: the e4m3 copy of the FP8 mode); rmult = rows of a stage relative to the bf16 stage (FP8 mode with R <= 2:
+// twice the rows in the same 32 KB - a stage costs the consumer one latency chain whatever it holds; R = 4 keeps the bf16
+// rows in 16 KB stages: 32 accumulators per lane would not fit the reduction tree).
 template <int EPI>
 __device__ __forceinline__ void mega_produce(const GemvArgs& a, unsigned char* ring, uint64_t* full_bar, uint64_t* empty_bar, int S, int& gst,
-                                             uint64_t pol, int lane, int wsz = 2) {
+                                             uint64_t pol, int lane, int wsz = 2, int rmult = 1) {
   constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
-  const int K = a.K, row_bytes = K * wsz, RPS = kMegaStageBytes / (K * 2);
-  const uint32_t stage_bytes = (uint32_t)(RPS * row_bytes);   // == kMegaStageBytes for bf16, half of it for e4m3
+  const int K = a.K, row_bytes = K * wsz, RPS = kMegaStageBytes / (K * 2) * rmult;
+  const uint32_t stage_bytes = (uint32_t)(RPS * row_bytes);   // == kMegaStageBytes for bf16 and for e4m3 with twice the rows (rmult = 2)
   const unsigned char* W8 = reinterpret_cast<const unsigned char*>(a.W);
   int u_begin, nrows;
   mega_slice<EPI>(a, u_begin, nrows);
@@ -887,10 +888,10 @@ __device__ __forceinline__ void mega_consume(const GemvArgs& a, unsigned char* r
   constexpr bool kPairs = (EPI == EPI_SILU || EPI == EPI_QKV);
   constexpr int Kc = NC * 256;
   constexpr int kWsz = F8 ? 1 : 2;                             // bytes per weight
-  constexpr uint32_t kStage = kMegaStageBytes / (F8 ? 2 : 1);  // a stage holds the same rows in both modes
   const int K = a.K, row_bytes = K * kWsz;
   const int KS = K / Kc;
   const int RPS = (kMW / KS) * RW;
+  const uint32_t kStage = F8 ? (uint32_t)(RPS * row_bytes) : (uint32_t)kMegaStageBytes;   // FP8: 16 KB (RW as bf16) or 32 KB (RW doubled)
   int u_begin, nrows;
   mega_slice<EPI>(a, u_begin, nrows);
   const int nstage = (nrows + RPS - 1) / RPS;
@@ -1743,7 +1744,8 @@ __device__ __forceinline__ void mega_fill(GemvArgs& a, const MegaArgs& m, int R)
 template <int R, int MODE>
 __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __grid_constant__ MegaArgs m) {
   constexpr bool TC = MODE == 1, F8 = MODE == 2;
-  constexpr int kStage = kMegaStageBytes / (F8 ? 2 : 1), kWsz = F8 ? 1 : 2;
+  constexpr int RM = (F8 && R <= 2) ? 2 : 1;                   // FP8 mode: rows of a ring stage relative to bf16 (see mega_produce)
+  constexpr int kStage = kMegaStageBytes / (F8 ? 2 : 1) * RM, kWsz = F8 ? 1 : 2;
   extern __shared__ __align__(128) unsigned char smem_m[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tc_bar[2];
   __shared__ float red[2][kMW][4];
@@ -1798,13 +1800,13 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       }
       mega_fill(a, m, R);
       a.W = L.in_proj; a.N = nqkv; a.K = m.D;
-      mega_produce<EPI_QKV>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
+      mega_produce<EPI_QKV>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz, RM);
       a.W = L.out_proj; a.N = m.D; a.K = qn;
-      mega_produce<EPI_STORE>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
+      mega_produce<EPI_STORE>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz, RM);
       a.W = L.fc1; a.N = 2 * m.F; a.K = m.D;
-      mega_produce<EPI_SILU>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
+      mega_produce<EPI_SILU>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz, RM);
       a.W = L.fc2; a.N = m.D; a.K = m.F;
-      mega_produce<EPI_RESID>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
+      mega_produce<EPI_RESID>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz, RM);
     }
     if (TC) {
       mega_produce_tc(m.heads_t, m.tg[TG_HEADS], m.D, ring, full_bar, empty_bar, S, gst, pol, lane);
@@ -1812,7 +1814,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
     }
     mega_fill(a, m, R);
     a.W = m.heads; a.N = m.QV; a.K = m.D;
-    mega_produce<EPI_HEADS>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz);
+    mega_produce<EPI_HEADS>(a, ring, full_bar, empty_bar, S, gst, pol, lane, kWsz, RM);
     return;
   }
 
@@ -1902,7 +1904,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       mega_scan_prefetch(m, L, has_unit ? (int)blockIdx.x : -1, attn_scratch);
       {
         unsigned long long* slot = MEGA_STAMP_SLOT();
-        mega_consume<R, 2, 4, PRO_NORM, EPI_STORE, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.zxt, TAG(ph),
+        mega_consume<R, 2, 4, PRO_NORM, EPI_STORE>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.zxt, TAG(ph),
                                                    nullptr, nullptr, nullptr, slot, 1);
       }
       MEGA_STAMP(); ++ph;
@@ -1919,7 +1921,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       a.W = L.out_proj; a.N = m.D; a.K = m.d_inner; a.ldx = 2 * m.d_inner; a.ldy = m.D; a.ldr = m.D; a.nw = nbuf + 2 * m.D; a.nb = nullptr;
       {
         unsigned long long* slot = MEGA_STAMP_SLOT();
-        mega_consume<R, 2, 4, PRO_GATED, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ygt, TAG(ph - 1), m.xt, TAG(ph),
+        mega_consume<R, 2, 4, PRO_GATED, EPI_RESID>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ygt, TAG(ph - 1), m.xt, TAG(ph),
                                                     m.xt, nullptr, nullptr, slot, 1, nullptr, nullptr, m.ygt + m.d_inner, 2 * m.d_inner, TAG(ph - 1));
       }
       MEGA_STAMP(); ++ph;
@@ -1937,7 +1939,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
         mega_consume_tc<R, 1, PRO_NORM, EPI_QKV>(a, m.tg[TG_QKV], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
                                                  nullptr, TAG(ph), nullptr, 0u, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
       else
-      mega_consume<R, 2, 4, PRO_NORM, EPI_QKV, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
+      mega_consume<R, 2, 4 * RM, PRO_NORM, EPI_QKV, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, TAG(ph),
                                                nullptr, m.qt, m.kvt, slot, 1, &qkv_pre, (stamping && li == 1) ? m.timeline + 200 : nullptr);
     }
     const int ph_in = ph;                                      // x was last written by phase ph_in - 1 (embedding or the previous fc2)
@@ -1968,7 +1970,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
                                                        TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph_in - 1), nullptr, nullptr, slot, 0, nullptr,
                                                        (stamping && li == 1) ? m.timeline + 208 : nullptr);
           else
-          mega_consume<R, 2, 4, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane, src, TAG(ph - 1), m.xt, TAG(ph),
+          mega_consume<R, 2, 4 * RM, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, g2, true, warp, lane, src, TAG(ph - 1), m.xt, TAG(ph),
                                                      m.xt, nullptr, nullptr, slot);
         } else {
           uint32_t* dst = (src == m.y1t) ? m.ayt : m.y1t;
@@ -1976,7 +1978,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
             mega_consume_tc<R, 1, PRO_NONE, EPI_STORE>(a, m.tg[TG_OUT], ring, part, full_bar, empty_bar, ts, red, S, g2, false, warp, lane, src,
                                                        TAG(ph - 1), dst, TAG(ph), nullptr, 0u, nullptr, nullptr, slot, 0, nullptr);
           else
-          mega_consume<R, 2, 4, PRO_NONE, EPI_STORE, F8>(a, ring, part, full_bar, empty_bar, red, S, g2, false, warp, lane, src, TAG(ph - 1), dst, TAG(ph),
+          mega_consume<R, 2, 4 * RM, PRO_NONE, EPI_STORE, F8>(a, ring, part, full_bar, empty_bar, red, S, g2, false, warp, lane, src, TAG(ph - 1), dst, TAG(ph),
                                                      nullptr, nullptr, nullptr, slot);
           src = dst;
         }
@@ -1994,7 +1996,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
         mega_consume_tc<R, 1, PRO_NORM, EPI_SILU>(a, m.tg[TG_FC1], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
                                                   m.ht, TAG(ph), nullptr, 0u, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 216 : nullptr);
       else
-      mega_consume<R, 2, 4, PRO_NORM, EPI_SILU, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
+      mega_consume<R, 2, 4 * RM, PRO_NORM, EPI_SILU, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), m.ht, TAG(ph),
                                                 nullptr, nullptr, nullptr, slot, 0, nullptr, (stamping && li == 1) ? m.timeline + 220 : nullptr);
     }
     MEGA_STAMP(); ++ph;
@@ -2014,10 +2016,10 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
           mega_consume_tc<R, 1, PRO_NONE, EPI_RESID>(a, m.tg[TG_FC2], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.ht,
                                                      TAG(ph - 1), m.xt, TAG(ph), m.xt, TAG(ph - 2), nullptr, nullptr, slot, 0, nullptr);
       } else if (m.F == 8192)
-        mega_consume<R, 4, 2, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
+        mega_consume<R, 4, 2 * RM, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
                                                    m.xt, nullptr, nullptr, slot);
       else
-        mega_consume<R, 2, 4, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
+        mega_consume<R, 2, 4 * RM, PRO_NONE, EPI_RESID, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.ht, TAG(ph - 1), m.xt, TAG(ph),
                                                    m.xt, nullptr, nullptr, slot);
     }
     MEGA_STAMP(); ++ph;
@@ -2031,7 +2033,7 @@ __global__ void __launch_bounds__((kMW + 1) * 32, 1) decode_step_kernel(const __
       mega_consume_tc<R, 1, PRO_NORM, EPI_HEADS>(a, m.tg[TG_HEADS], ring, part, full_bar, empty_bar, ts, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1),
                                                  nullptr, 0u, nullptr, 0u, nullptr, nullptr, slot, 0, nullptr);
     else
-    mega_consume<R, 2, 4, PRO_NORM, EPI_HEADS, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, 0u,
+    mega_consume<R, 2, 4 * RM, PRO_NORM, EPI_HEADS, F8>(a, ring, part, full_bar, empty_bar, red, S, gst, true, warp, lane, m.xt, TAG(ph - 1), nullptr, 0u,
                                                nullptr, nullptr, nullptr, slot);
   }
   MEGA_STAMP();
@@ -2869,7 +2871,11 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
   ZB_REQUIRE(ctx, cfg_scale != 1.0f, "persistent decode expects CFG rows");
   const int grid = ctx->num_sms;
   // partial-sum buffer: the largest padded row count x k-slices over all matrices of the step
+  // FP8 mode (decided below from the same inputs): R <= 2 doubles the rows of a stage (RW x 2 in the kernel's instantiations)
+  const bool f8_early = model->n_mamba == 0 && zb_mega_fp8_enabled(model, R) && model->f8w && model->f8w_valid;
+  const int rm = (f8_early && R <= 2) ? 2 : 1;
   auto part_need = [&](int nunits, bool pairs, int K, int NC, int RW) {
+    RW *= rm;
     const int KS = K / (NC * 256), RPS = (kMW / KS) * RW;
     const int rows = ((nunits + grid - 1) / grid) * (pairs ? 2 : 1);
     return (size_t)((rows + RPS - 1) / RPS * RPS) * KS * R * sizeof(float);
@@ -2903,7 +2909,8 @@ zb_status zb_launch_decode_step(zb_ctx* ctx, const zb_model* model, const zb_cac
     m.heads = (const bf16*)((const char*)model->f8w + fp.heads_off);
     m.s_heads = (const float*)((const char*)model->f8w + fp.scales_off) + fp.heads_soff;
   }
-  const size_t stage_bytes = f8 ? kMegaStageBytes / 2 : kMegaStageBytes;
+  ZB_REQUIRE(ctx, f8 == f8_early, "internal: FP8 mode decided two ways");
+  const size_t stage_bytes = f8 ? (size_t)(kMegaStageBytes / 2) * rm : (size_t)kMegaStageBytes;
   const size_t attn_bytes = kMegaAttnBytes + (size_t)4 * d.d_model * sizeof(bf16);   // attention tiles + two norm-parameter buffers
   const size_t avail = 227 * 1024 - 2048 - (tc ? kMegaTcImageBytes + 1024 : 0);      // (tc: activation image, 1024-byte alignment of the ring)
   int stages = (int)((avail - pb - attn_bytes) / stage_bytes);

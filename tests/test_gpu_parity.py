@@ -374,6 +374,9 @@ def test_fp8_mode_full_size(full_model, monkeypatch):
     try:
         compared, worst = _compare_fp8_sessions(model, TRANSFORMER_DIMS, 1, 40, 16, monkeypatch, 1.0)
         assert compared >= 3
+        # batch 2 (R = 4 rows: 16 KB stages with the bf16 row geometry; scripts/fp8_b2_check.py is the same comparison stand-alone)
+        compared, worst = _compare_fp8_sessions(model, TRANSFORMER_DIMS, 2, 40, 8, monkeypatch, 1.0)
+        assert compared >= 6
     finally:
         model.load_state_dict(w)
     cond = make_conditioning(2, 40, TRANSFORMER_DIMS["d_model"], seed=4).to(DEV)

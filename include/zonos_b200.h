@@ -109,7 +109,8 @@ typedef struct {
 ZB_API zb_status zb_model_create(zb_ctx* ctx, const zb_model_desc* desc, zb_model** out);
 ZB_API zb_status zb_model_destroy(zb_model* model);
 /* The caller has modified weights in place (same pointers, e.g. nn.Module.load_state_dict after the first call): copies
- * the library derived from them (the tile-ordered decode weights) are rebuilt by the next zb_generate_begin.  Replaces
+ * the library derived from them (the tile-ordered decode weights of ZB_MEGA_TC=1, the e4m3 copy of the opt-in FP8 mode
+ * ZB_FP8=1 - both environment switches read at zb_generate_begin) are rebuilt by the next zb_generate_begin.  Replaces
  * nothing in the reference - its torch modules read the live parameters (zonos/model.py:160-175). */
 ZB_API zb_status zb_model_weights_changed(zb_model* model);
 

@@ -216,3 +216,31 @@ def test_fp8_quantiser_contract_on_the_host():
         assert torch.equal(torch.sign(b)[big], torch.sign(a)[big])
     assert touched == 4 * TINY_DIMS["n_layer"] + 1
     assert float(d1["fused_heads.weight"][3].abs().max()) == 0.0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm): rank 0 prints ONE JSON line with the contract keys, running the
+    unmodified reference from oracle/_ref when build() staged it (kind "reference") and the oracle port otherwise; every other
+    rank exits 0 without work.  One layer and four frames: this checks the plumbing, not a number."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-frames", "4", "--layers", "1"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "audio_seconds_per_second" and d["higher_is_better"] is True and d["value"] > 0
+    staged = os.path.isdir(os.path.join(root, "oracle", "_ref", "zonos"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "workload" in d["config"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=root)
+    assert other.returncode == 0 and other.stdout.strip() == ""
